@@ -1,0 +1,1143 @@
+// jade_gpu.cu -- the C ABI of include/jade_gpu.h on top of the sm_100a kernels in jade_kernels.cuh.
+//
+// There is NO CPU fallback: every compute entry point launches CUDA kernels or fails with JADE_ERR_NOGPU /
+// JADE_ERR_CUDA.  The only host arithmetic is one-off table generation (window, palette, twiddles, row maps),
+// which the reference also does on the host at reconfiguration time.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/jade_gpu.h"
+#include "jade_host_tables.h"
+#include "jade_kernels.cuh"
+
+using jade::KParams;
+
+namespace {
+
+thread_local std::string t_last_error;
+
+typedef void (*kernel_fn)(const KParams);
+
+struct KernelChoice {
+    kernel_fn fn = nullptr;
+    int threads = 0;
+    int smem = 0;
+    int blocks_per_sm = 1;
+    int units_per_block = 1; // frames a block processes per loop iteration
+    char name[32] = {0};
+    int family = 0; // 0 warp, 1 cta, 2 cta2
+};
+
+template <int T>
+kernel_fn pick_warp(bool multi, bool pool)
+{
+    if (multi) return pool ? (kernel_fn)jade::stft_warp_kernel<T, true, true> : (kernel_fn)jade::stft_warp_kernel<T, true, false>;
+    return pool ? (kernel_fn)jade::stft_warp_kernel<T, false, true> : (kernel_fn)jade::stft_warp_kernel<T, false, false>;
+}
+template <int R1>
+kernel_fn pick_cta(bool multi, bool pool)
+{
+    if (multi) return pool ? (kernel_fn)jade::stft_cta_kernel<R1, true, true> : (kernel_fn)jade::stft_cta_kernel<R1, true, false>;
+    return pool ? (kernel_fn)jade::stft_cta_kernel<R1, false, true> : (kernel_fn)jade::stft_cta_kernel<R1, false, false>;
+}
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    int ensure(size_t n)
+    {
+        if (n <= bytes) return 0;
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+        if (cudaMalloc(&p, n) != cudaSuccess) return -1;
+        bytes = n;
+        return 0;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+};
+struct PinBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    int ensure(size_t n)
+    {
+        if (n <= bytes) return 0;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        bytes = 0;
+        if (cudaHostAlloc(&p, n, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) return -1;
+        bytes = n;
+        return 0;
+    }
+    void release()
+    {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        bytes = 0;
+    }
+};
+
+constexpr int kStageSlots = 8;
+constexpr int kPipe = 3; // batch pipeline depth
+
+} // namespace
+
+struct jade_engine {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    cudaStream_t pipe_stream[kPipe] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+    bool timed = false;
+    std::string err;
+    std::mutex mu;
+    std::atomic<long long> launches{0};
+
+    bool configured = false;
+    jade_config cfg{};
+    int N = 0, M = 0, B = 0, R = 0, W = 0;
+    int k_lo = 0, k_hi = 0;
+    KernelChoice kc;
+    bool multi = false, pooled = false;
+
+    // tables
+    std::vector<float> h_window;       // unit-RMS reference window
+    std::vector<int32_t> h_palette;    // 0x00RRGGBB
+    jade_host::ValueRange range;
+    DevBuf d_window, d_twI, d_twP, d_twA, d_twH, d_palette, d_rowbins, d_scratch_e, d_scratch_p;
+    int npal = 0;
+
+    // streaming
+    DevBuf d_hist, d_dbring;
+    PinBuf h_pixring, h_stage;
+    long long hist_cap = 0, hist_fill = 0, hist_base_abs = 0;
+    long long pushed = 0;       // samples pushed per channel
+    long long frames_done = 0;  // frames analysed (or skipped while paused): next frame index
+    long long emitted = 0;      // columns published to the ring (the reference's running m_memCounter)
+    long long fetched = 0;      // columns handed to fetch
+    int stage_slot = 0;
+    size_t stage_slot_bytes = 0;
+    cudaEvent_t stage_ev[kStageSlots] = {};
+    cudaEvent_t last_push_ev = nullptr;
+    bool paused = false;
+
+    // batch pipeline
+    DevBuf pipe_in[kPipe], pipe_pix[kPipe], pipe_db[kPipe];
+    PinBuf pipe_hin[kPipe], pipe_hpix[kPipe], pipe_hdb[kPipe];
+    cudaEvent_t pipe_done[kPipe] = {};
+};
+
+namespace {
+
+int fail(jade_engine* e, int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    t_last_error = buf;
+    if (e) e->err = buf;
+    return code;
+}
+#define CU(e, call)                                                                                          \
+    do {                                                                                                     \
+        cudaError_t _r = (call);                                                                             \
+        if (_r != cudaSuccess)                                                                               \
+            return fail((e), JADE_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_r), __FILE__, __LINE__); \
+    } while (0)
+
+bool is_pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
+
+int upload(jade_engine* e, DevBuf& b, const void* src, size_t bytes)
+{
+    if (b.ensure(bytes ? bytes : 16)) return fail(e, JADE_ERR_CUDA, "cudaMalloc(%zu) failed", bytes);
+    if (bytes) CU(e, cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, e->stream));
+    CU(e, cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+int choose_kernel(jade_engine* e)
+{
+    KernelChoice kc;
+    const int N = e->N;
+    const bool mu = e->multi, po = e->pooled;
+    if (N <= 2048) {
+        const int T = N / 64;
+        kc.family = 0;
+        kc.threads = jade::WARP_KERNEL_WARPS * 32;
+        kc.units_per_block = jade::WARP_KERNEL_WARPS * (32 / T);
+        snprintf(kc.name, sizeof kc.name, "warp<%d>", T);
+        switch (T) {
+        case 1: kc.fn = pick_warp<1>(mu, po); kc.smem = jade::WarpCfg<1>::smem_bytes(e->npal, po); break;
+        case 2: kc.fn = pick_warp<2>(mu, po); kc.smem = jade::WarpCfg<2>::smem_bytes(e->npal, po); break;
+        case 4: kc.fn = pick_warp<4>(mu, po); kc.smem = jade::WarpCfg<4>::smem_bytes(e->npal, po); break;
+        case 8: kc.fn = pick_warp<8>(mu, po); kc.smem = jade::WarpCfg<8>::smem_bytes(e->npal, po); break;
+        case 16: kc.fn = pick_warp<16>(mu, po); kc.smem = jade::WarpCfg<16>::smem_bytes(e->npal, po); break;
+        case 32: kc.fn = pick_warp<32>(mu, po); kc.smem = jade::WarpCfg<32>::smem_bytes(e->npal, po); break;
+        default: return fail(e, JADE_ERR_ARG, "unsupported fft_size %d", N);
+        }
+    } else if (N <= 32768) {
+        const int R1 = N / 2048;
+        kc.family = 1;
+        kc.threads = 32 * R1;
+        snprintf(kc.name, sizeof kc.name, "cta<%d>", R1);
+        switch (R1) {
+        case 2: kc.fn = pick_cta<2>(mu, po); kc.smem = jade::CtaCfg<2>::smem_bytes(e->npal, po); break;
+        case 4: kc.fn = pick_cta<4>(mu, po); kc.smem = jade::CtaCfg<4>::smem_bytes(e->npal, po); break;
+        case 8: kc.fn = pick_cta<8>(mu, po); kc.smem = jade::CtaCfg<8>::smem_bytes(e->npal, po); break;
+        case 16: kc.fn = pick_cta<16>(mu, po); kc.smem = jade::CtaCfg<16>::smem_bytes(e->npal, po); break;
+        default: return fail(e, JADE_ERR_ARG, "unsupported fft_size %d", N);
+        }
+    } else if (N == 65536) {
+        kc.family = 2;
+        kc.threads = 32 * 16;
+        snprintf(kc.name, sizeof kc.name, "cta2<16>");
+        kc.fn = mu ? (kernel_fn)jade::stft_cta2_kernel<16, true> : (kernel_fn)jade::stft_cta2_kernel<16, false>;
+        kc.smem = jade::CtaCfg<16>::smem_bytes(e->npal, false);
+    } else {
+        return fail(e, JADE_ERR_ARG, "unsupported fft_size %d (power of two in [64,65536])", N);
+    }
+    CU(e, cudaFuncSetAttribute((const void*)kc.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kc.smem));
+    int occ = 0;
+    CU(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)kc.fn, kc.threads, kc.smem));
+    if (occ < 1) return fail(e, JADE_ERR_CUDA, "kernel %s does not fit on an SM (smem %d)", kc.name, kc.smem);
+    kc.blocks_per_sm = occ;
+    e->kc = kc;
+    return 0;
+}
+
+long long frame_start_abs(const jade_config& c, long long j)
+{
+    return (j / c.frames_per_block) * (long long)c.block_stride + (j % c.frames_per_block) * (long long)c.hop - c.preroll;
+}
+// number of columns available once `pushed` samples per channel exist
+long long columns_available(const jade_config& c, long long pushed)
+{
+    const long long N = c.fft_size, fb = c.frames_per_block, S = c.block_stride;
+    if (c.emit_mode == JADE_EMIT_BLOCK) {
+        // block b complete when its last frame's samples are in: b*S + (fb-1)*hop - preroll + N <= pushed, and -- like
+        // the reference, which consumes whole N-sample blocks -- when the block itself has been pushed entirely
+        const long long last_off = (fb - 1) * (long long)c.hop - c.preroll + N;
+        const long long need0 = std::max<long long>(last_off, S - c.preroll + N);
+        if (pushed < need0) return 0;
+        return ((pushed - need0) / S + 1) * fb;
+    }
+    // HOP mode: largest j with start(j)+N <= pushed
+    long long lo = 0, hi = (pushed / std::max(1, c.hop) + 2) * 1 + fb + 2;
+    // start() is monotone in j
+    while (frame_start_abs(c, hi) + N <= pushed) hi *= 2;
+    while (lo < hi) {
+        const long long mid = (lo + hi) / 2;
+        if (frame_start_abs(c, mid) + N <= pushed) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+void fill_params(jade_engine* e, KParams& P)
+{
+    memset(&P, 0, sizeof P);
+    const jade_config& c = e->cfg;
+    P.N = e->N;
+    P.M = e->M;
+    P.B = e->B;
+    P.hop = c.hop;
+    P.fb = c.frames_per_block;
+    P.bstride = c.block_stride;
+    P.preroll = c.preroll;
+    P.channels = c.channels;
+    P.mix_mode = c.mix_mode;
+    P.window = (const float*)e->d_window.p;
+    P.twI = (const jade::cpx*)e->d_twI.p;
+    P.twP = (const jade::cpx*)e->d_twP.p;
+    P.twA = (const jade::cpx*)e->d_twA.p;
+    P.twH = (const jade::cpx*)e->d_twH.p;
+    P.palette = (const uint32_t*)e->d_palette.p;
+    P.npal = e->npal;
+    P.pmin = e->range.mn;
+    P.pmax = e->range.mx;
+    P.pmaxc = e->range.maxclamp();
+    P.pmult = e->range.mult;
+    P.db_precise = c.db_precise;
+    P.pooled = e->pooled ? 1 : 0;
+    P.R = e->R;
+    P.k_lo = e->k_lo;
+    P.k_hi = e->k_hi;
+    P.flip = c.flip_y;
+    P.row_bins = (const jade::i2*)e->d_rowbins.p;
+    P.scratch_e = (jade::cpx*)e->d_scratch_e.p;
+    P.scratch_p = (float*)e->d_scratch_p.p;
+}
+
+// grid size: persistent, a multiple of the SM count when there is enough work
+int grid_for(jade_engine* e, long long frames)
+{
+    const long long blocks_needed = (frames + e->kc.units_per_block - 1) / e->kc.units_per_block;
+    const long long cap = (long long)e->sm_count * e->kc.blocks_per_sm;
+    return (int)std::max<long long>(1, std::min(blocks_needed, cap));
+}
+
+int launch_stft(jade_engine* e, KParams& P, cudaStream_t st)
+{
+    const long long frames = (long long)P.ncols * P.nstreams;
+    if (frames <= 0) return 0;
+    const int grid = grid_for(e, frames);
+    if (e->kc.family == 2) {
+        const size_t need_e = (size_t)grid * (e->N / 4 + 1) * sizeof(jade::cpx);
+        const size_t need_p = (size_t)grid * (e->N / 2 + 1) * sizeof(float);
+        if (e->d_scratch_e.bytes < need_e || e->d_scratch_p.bytes < need_p)
+            return fail(e, JADE_ERR_STATE, "scratch not sized for grid %d", grid);
+    }
+    void* args[] = {(void*)&P};
+    CU(e, cudaLaunchKernel((const void*)e->kc.fn, dim3(grid), dim3(e->kc.threads), args, e->kc.smem, st));
+    e->launches++;
+    return 0;
+}
+
+uint32_t bake_pixel(int32_t rgb, int fmt)
+{
+    const uint32_t r = (rgb >> 16) & 255, g = (rgb >> 8) & 255, b = rgb & 255;
+    if (fmt == JADE_PIX_RGBA8) return 0xFF000000u | (b << 16) | (g << 8) | r; // bytes R,G,B,A on little endian
+    return 0xFF000000u | (r << 16) | (g << 8) | b;                           // Spectrogram.cpp:637
+}
+
+int upload_palette(jade_engine* e)
+{
+    std::vector<uint32_t> baked(e->h_palette.size());
+    for (size_t i = 0; i < baked.size(); ++i) baked[i] = bake_pixel(e->h_palette[i], e->cfg.pixel_format);
+    e->npal = (int)baked.size();
+    return upload(e, e->d_palette, baked.data(), baked.size() * 4);
+}
+
+int upload_window(jade_engine* e)
+{
+    jade_host::make_window(e->cfg.window, e->N, e->h_window);
+    // device copy: x 0.5 (real-FFT split without the 1/2) x sqrt(power_scale)
+    std::vector<float> w(e->h_window);
+    const float ps = e->cfg.power_scale;
+    const float g = (ps == 1.0f) ? 0.5f : 0.5f * std::sqrt(ps);
+    for (auto& v : w) v *= g;
+    return upload(e, e->d_window, w.data(), w.size() * 4);
+}
+
+int reset_stream_state(jade_engine* e)
+{
+    const jade_config& c = e->cfg;
+    // history: [preroll zeros | samples ...]
+    CU(e, cudaMemsetAsync(e->d_hist.p, 0, e->d_hist.bytes, e->stream));
+    e->hist_base_abs = -(long long)c.preroll;
+    e->hist_fill = c.preroll;
+    e->pushed = 0;
+    e->emitted = 0;
+    e->frames_done = 0;
+    e->fetched = 0;
+    // ring filled with -120 dB (Spectrogram.cpp:223); pixel ring with the colour of -120 dB
+    std::vector<float> init((size_t)e->W * e->B, -120.0f);
+    CU(e, cudaMemcpyAsync(e->d_dbring.p, init.data(), init.size() * 4, cudaMemcpyHostToDevice, e->stream));
+    CU(e, cudaStreamSynchronize(e->stream));
+    if (e->npal > 0) {
+        const int idx = jade_host::palette_index(-120.0f, e->range, e->npal);
+        const uint32_t px = bake_pixel(e->h_palette[idx], c.pixel_format);
+        uint32_t* p = (uint32_t*)e->h_pixring.p;
+        for (size_t i = 0; i < (size_t)e->W * e->R; ++i) p[i] = px;
+    }
+    return 0;
+}
+
+} // namespace
+
+// =========================================================================================================
+extern "C" {
+
+int jade_abi_version(void) { return JADE_ABI_VERSION; }
+
+int jade_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+const char* jade_last_error(jade_engine* e) { return e ? e->err.c_str() : t_last_error.c_str(); }
+
+int jade_create(int device, jade_engine** out)
+{
+    if (!out) return fail(nullptr, JADE_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t r = cudaGetDeviceCount(&n);
+    if (r != cudaSuccess || n <= 0)
+        return fail(nullptr, JADE_ERR_NOGPU, "no CUDA device (%s); libjade_gpu has no CPU fallback",
+                    r == cudaSuccess ? "count=0" : cudaGetErrorString(r));
+    if (device < 0 || device >= n) return fail(nullptr, JADE_ERR_ARG, "device %d out of range [0,%d)", device, n);
+    jade_engine* e = new jade_engine();
+    e->device = device;
+    CU(e, cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(e, cudaGetDeviceProperties(&prop, device));
+    e->sm_count = prop.multiProcessorCount;
+    CU(e, cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    for (int i = 0; i < kPipe; ++i) {
+        CU(e, cudaStreamCreateWithFlags(&e->pipe_stream[i], cudaStreamNonBlocking));
+        CU(e, cudaEventCreateWithFlags(&e->pipe_done[i], cudaEventDisableTiming));
+    }
+    CU(e, cudaEventCreate(&e->ev_t0));
+    CU(e, cudaEventCreate(&e->ev_t1));
+    for (int i = 0; i < kStageSlots; ++i) CU(e, cudaEventCreateWithFlags(&e->stage_ev[i], cudaEventDisableTiming));
+    CU(e, cudaEventCreateWithFlags(&e->last_push_ev, cudaEventDisableTiming));
+    // default palette: the component's (256 colours, kJade, -50..50 dB; Spectrogram.cpp:337,342)
+    e->h_palette.assign(256, 0);
+    jade_host::palette_build(JADE_PAL_JADE, 256, 0, e->h_palette.data());
+    e->range.set(-50.f, 50.f, 256);
+    *out = e;
+    return JADE_OK;
+}
+
+int jade_destroy(jade_engine* e)
+{
+    if (!e) return JADE_OK;
+    cudaSetDevice(e->device);
+    cudaDeviceSynchronize();
+    for (DevBuf* b : {&e->d_window, &e->d_twI, &e->d_twP, &e->d_twA, &e->d_twH, &e->d_palette, &e->d_rowbins,
+                      &e->d_scratch_e, &e->d_scratch_p, &e->d_hist, &e->d_dbring})
+        b->release();
+    e->h_pixring.release();
+    e->h_stage.release();
+    for (int i = 0; i < kPipe; ++i) {
+        e->pipe_in[i].release();
+        e->pipe_pix[i].release();
+        e->pipe_db[i].release();
+        e->pipe_hin[i].release();
+        e->pipe_hpix[i].release();
+        e->pipe_hdb[i].release();
+        if (e->pipe_stream[i]) cudaStreamDestroy(e->pipe_stream[i]);
+        if (e->pipe_done[i]) cudaEventDestroy(e->pipe_done[i]);
+    }
+    for (int i = 0; i < kStageSlots; ++i)
+        if (e->stage_ev[i]) cudaEventDestroy(e->stage_ev[i]);
+    if (e->last_push_ev) cudaEventDestroy(e->last_push_ev);
+    if (e->ev_t0) cudaEventDestroy(e->ev_t0);
+    if (e->ev_t1) cudaEventDestroy(e->ev_t1);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+    return JADE_OK;
+}
+
+int jade_config_default(jade_config* c)
+{
+    if (!c) return JADE_ERR_ARG;
+    memset(c, 0, sizeof *c);
+    c->sample_rate = 48000.f;
+    c->fft_size = 2048; // PluginProcessor.cpp:13
+    c->window = JADE_WIN_HANN;
+    c->channels = 2;
+    c->mix_mode = JADE_MIX_ABSMEAN;
+    c->row_map = JADE_ROWS_IDENTITY;
+    c->flip_y = 1;
+    c->pixel_format = JADE_PIX_ARGB32;
+    c->power_scale = 1.f;
+    c->memory_time_s = 10.f; // PluginProcessor.cpp:110
+    c->preroll = -1;
+    c->emit_mode = JADE_EMIT_BLOCK;
+    c->fmin = 0.f;
+    c->fmax = 20000.f;
+    return jade_config_set_feed_percent(c, 50); // PluginProcessor.cpp:112
+}
+
+int jade_config_set_feed_percent(jade_config* c, int percent)
+{
+    if (!c) return JADE_ERR_ARG;
+    float pct;
+    switch (percent) { // Spectrogram.cpp:189-211
+    case 100: pct = 100.0; c->frames_per_block = 1; break;
+    case 50: pct = 50.0; c->frames_per_block = 2; break;
+    case 25: pct = 25.0; c->frames_per_block = 4; break;
+    case 10: pct = 10.0; c->frames_per_block = 10; break;
+    default: return JADE_ERR_ARG;
+    }
+    c->hop = int(pct * 0.01 * size_t(c->fft_size) + 0.5); // Spectrogram.cpp:216
+    c->block_stride = c->fft_size;
+    return JADE_OK;
+}
+
+int jade_configure(jade_engine* e, const jade_config* cin)
+{
+    if (!e || !cin) return fail(e, JADE_ERR_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(e->mu);
+    CU(e, cudaSetDevice(e->device));
+    jade_config c = *cin;
+    if (!is_pow2(c.fft_size) || c.fft_size < 64 || c.fft_size > 65536)
+        return fail(e, JADE_ERR_ARG, "fft_size %d must be a power of two in [64,65536]", c.fft_size);
+    if (c.hop <= 0) return fail(e, JADE_ERR_ARG, "hop %d must be positive", c.hop);
+    if (c.channels < 1 || c.channels > 16) return fail(e, JADE_ERR_ARG, "channels %d out of [1,16]", c.channels);
+    if (c.mix_mode < 0 || c.mix_mode > JADE_MIX_RIGHT) return fail(e, JADE_ERR_ARG, "bad mix_mode %d", c.mix_mode);
+    if (c.window < 0 || c.window > JADE_WIN_HANNPOISSON) return fail(e, JADE_ERR_ARG, "bad window %d", c.window);
+    if (c.frames_per_block < 1) c.frames_per_block = 1;
+    if (c.block_stride <= 0) c.block_stride = c.hop * c.frames_per_block;
+    if (c.preroll < 0) c.preroll = c.fft_size;
+    if (c.power_scale <= 0.f) c.power_scale = 1.f;
+    if (c.sample_rate <= 0.f) return fail(e, JADE_ERR_ARG, "sample_rate must be positive");
+    if (c.max_push <= 0) c.max_push = c.fft_size;
+    if ((long long)(c.frames_per_block - 1) * c.hop > c.block_stride + c.fft_size)
+        return fail(e, JADE_ERR_ARG, "frames_per_block*hop exceeds the block");
+
+    e->configured = false;
+    e->cfg = c;
+    e->N = c.fft_size;
+    e->M = e->N / 2;
+    e->B = e->M + 1;
+    // ring width: Spectrogram.cpp:217  int(mem_s*fs/hop + 0.5) with float products
+    if (c.ring_columns > 0) e->W = c.ring_columns;
+    else {
+        const float mem = c.memory_time_s > 0.f ? c.memory_time_s : 1.0f;
+        e->W = int(mem * c.sample_rate / c.hop + 0.5);
+        if (e->W < 1) e->W = 1;
+    }
+    e->cfg.ring_columns = e->W;
+
+    // rows
+    e->pooled = false;
+    e->k_lo = 0;
+    e->k_hi = e->B;
+    std::vector<jade::i2> rb;
+    if (c.row_map == JADE_ROWS_LINEAR_CROP) {
+        jade_host::linear_crop(c.sample_rate, e->B, c.fmin, c.fmax, e->k_lo, e->k_hi);
+        e->R = e->k_hi - e->k_lo;
+    } else if (c.row_map == JADE_ROWS_LOG_MAXPOOL) {
+        if (c.rows < 1) return fail(e, JADE_ERR_ARG, "rows must be >= 1 for LOG_MAXPOOL");
+        std::vector<int32_t> lo, hi;
+        jade_host::log_rows(c.sample_rate, e->N, c.rows, c.fmin, c.fmax, lo, hi);
+        rb.resize(c.rows);
+        for (int r = 0; r < c.rows; ++r) rb[r] = {lo[r], hi[r]};
+        e->R = c.rows;
+        e->pooled = true;
+    } else if (c.row_map == JADE_ROWS_IDENTITY) {
+        e->R = e->B;
+    } else {
+        return fail(e, JADE_ERR_ARG, "bad row_map %d", c.row_map);
+    }
+    e->cfg.rows = e->R;
+    e->multi = c.channels > 1 || c.mix_mode == JADE_MIX_MIN;
+
+    // tables
+    if (int r = upload_window(e)) return r;
+    if (int r = upload_palette(e)) return r;
+    if (int r = upload(e, e->d_rowbins, rb.data(), rb.size() * sizeof(jade::i2))) return r;
+    std::vector<jade_host::cpxf> tw;
+    jade_host::twiddles(e->N, e->M + 1, 1, tw); // W_N^k, k = 0..M
+    if (int r = upload(e, e->d_twP, tw.data(), tw.size() * 8)) return r;
+    if (e->N <= 2048) {
+        const int T = e->N / 64;
+        jade_host::twiddle_matrix(32 * T, 32, T, tw);
+        if (int r = upload(e, e->d_twI, tw.data(), tw.size() * 8)) return r;
+    } else {
+        jade_host::twiddle_matrix(1024, 32, 32, tw);
+        if (int r = upload(e, e->d_twI, tw.data(), tw.size() * 8)) return r;
+        const int Mfft = (e->N == 65536) ? e->N / 4 : e->M; // complex points of the CTA transform
+        const int R1 = Mfft / 1024;
+        jade_host::twiddle_matrix(Mfft, R1, 1024, tw);
+        if (int r = upload(e, e->d_twA, tw.data(), tw.size() * 8)) return r;
+        if (e->N == 65536) {
+            jade_host::twiddles(e->N / 2, e->N / 4 + 1, 1, tw); // split twiddles of the half-size real FFTs
+            if (int r = upload(e, e->d_twH, tw.data(), tw.size() * 8)) return r;
+        }
+    }
+    if (int r = choose_kernel(e)) return r;
+    if (e->kc.family == 2) {
+        const size_t g = (size_t)e->sm_count * e->kc.blocks_per_sm;
+        if (e->d_scratch_e.ensure(g * (e->N / 4 + 1) * sizeof(jade::cpx)) || e->d_scratch_p.ensure(g * (e->N / 2 + 1) * 4))
+            return fail(e, JADE_ERR_CUDA, "scratch allocation failed");
+    }
+
+    // streaming buffers
+    const long long span = (long long)e->N + c.block_stride + (long long)(c.frames_per_block) * c.hop;
+    e->hist_cap = 2 * span + 2LL * c.max_push + 64 + c.preroll;
+    e->hist_cap = (e->hist_cap + 3) & ~3LL;
+    if (e->d_hist.ensure((size_t)e->hist_cap * c.channels * 4)) return fail(e, JADE_ERR_CUDA, "history allocation failed");
+    if (e->d_dbring.ensure((size_t)e->W * e->B * 4)) return fail(e, JADE_ERR_CUDA, "ring allocation failed");
+    if (e->h_pixring.ensure((size_t)e->W * e->R * 4)) return fail(e, JADE_ERR_CUDA, "pinned ring allocation failed");
+    e->stage_slot_bytes = ((size_t)c.max_push * c.channels * 4 + 255) & ~(size_t)255;
+    if (e->h_stage.ensure(e->stage_slot_bytes * kStageSlots)) return fail(e, JADE_ERR_CUDA, "pinned staging allocation failed");
+    if (int r = reset_stream_state(e)) return r;
+    e->configured = true;
+    return JADE_OK;
+}
+
+int jade_get_config(jade_engine* e, jade_config* out)
+{
+    if (!e || !out) return JADE_ERR_ARG;
+    if (!e->configured) return fail(e, JADE_ERR_STATE, "engine not configured");
+    *out = e->cfg;
+    return JADE_OK;
+}
+
+int jade_set_pause(jade_engine* e, int on)
+{
+    if (!e) return JADE_ERR_ARG;
+    std::lock_guard<std::mutex> lk(e->mu);
+    e->paused = on != 0;
+    return JADE_OK;
+}
+
+int jade_set_window(jade_engine* e, int window)
+{
+    if (!e || window < 0 || window > JADE_WIN_HANNPOISSON) return fail(e, JADE_ERR_ARG, "bad window");
+    if (!e->configured) return fail(e, JADE_ERR_STATE, "engine not configured");
+    std::lock_guard<std::mutex> lk(e->mu);
+    CU(e, cudaSetDevice(e->device));
+    CU(e, cudaStreamSynchronize(e->stream));
+    e->cfg.window = window;
+    return upload_window(e);
+}
+
+int jade_get_window(jade_engine* e, float* out, int n)
+{
+    if (!e || !out) return JADE_ERR_ARG;
+    if (!e->configured) return fail(e, JADE_ERR_STATE, "engine not configured");
+    if (n != e->N) return fail(e, JADE_ERR_ARG, "window length %d != fft_size %d", n, e->N);
+    memcpy(out, e->h_window.data(), (size_t)n * 4);
+    return JADE_OK;
+}
+
+int jade_reset(jade_engine* e)
+{
+    if (!e) return JADE_ERR_ARG;
+    if (!e->configured) return fail(e, JADE_ERR_STATE, "engine not configured");
+    std::lock_guard<std::mutex> lk(e->mu);
+    CU(e, cudaSetDevice(e->device));
+    CU(e, cudaStreamSynchronize(e->stream));
+    return reset_stream_state(e);
+}
+
+// ---- palette ------------------------------------------------------------------------------------------
+int jade_palette_build(int scheme, int n, int invert, int32_t* table)
+{
+    if (!table || n < 1 || scheme < 0 || scheme > JADE_PAL_JADE) return JADE_ERR_ARG;
+    jade_host::palette_build(scheme, n, invert, table);
+    return JADE_OK;
+}
+
+int jade_set_palette(jade_engine* e, const int32_t* rgb, int n)
+{
+    if (!e || !rgb || n < 1 || n > 65536) return fail(e, JADE_ERR_ARG, "bad palette");
+    std::lock_guard<std::mutex> lk(e->mu);
+    CU(e, cudaSetDevice(e->device));
+    const bool resize = (int)e->h_palette.size() != n;
+    e->h_palette.assign(rgb, rgb + n);
+    e->range.mult = float(n) / (e->range.mx - e->range.mn); // CColorpalette.cpp:55-61 setNrOfColors
+    if (e->configured) {
+        CU(e, cudaStreamSynchronize(e->stream));
+        for (int i = 0; i < kPipe; ++i) CU(e, cudaStreamSynchronize(e->pipe_stream[i]));
+        if (int r = upload_palette(e)) return r;
+        if (resize)
+            if (int r = choose_kernel(e)) return r; // shared-memory size depends on the table length
+    } else {
+        e->npal = n;
+    }
+    return JADE_OK;
+}
+
+int jade_set_palette_scheme(jade_engine* e, int scheme, int n, int invert)
+{
+    if (!e || n < 1 || n > 65536 || scheme < 0 || scheme > JADE_PAL_JADE) return fail(e, JADE_ERR_ARG, "bad palette scheme");
+    std::vector<int32_t> t(n, 0);
+    jade_host::palette_build(scheme, n, invert, t.data());
+    return jade_set_palette(e, t.data(), n);
+}
+
+int jade_set_value_range(jade_engine* e, float mn, float mx)
+{
+    if (!e) return JADE_ERR_ARG;
+    std::lock_guard<std::mutex> lk(e->mu);
+    e->range.set(mn, mx, (int)e->h_palette.size());
+    return JADE_OK;
+}
+
+int jade_get_value_range(jade_engine* e, float* mn, float* mx, float* mult)
+{
+    if (!e) return JADE_ERR_ARG;
+    if (mn) *mn = e->range.mn;
+    if (mx) *mx = e->range.mx;
+    if (mult) *mult = e->range.mult;
+    return JADE_OK;
+}
+
+int jade_lookup_color(jade_engine* e, float v, int32_t* rgb)
+{
+    if (!e || !rgb || e->h_palette.empty()) return JADE_ERR_ARG;
+    *rgb = e->h_palette[jade_host::palette_index(v, e->range, (int)e->h_palette.size())];
+    return JADE_OK;
+}
+
+int jade_linear_crop(float fs, int bins, float fmin, float fmax, int* k_lo, int* k_hi)
+{
+    if (!k_lo || !k_hi || bins < 1 || fs <= 0.f) return JADE_ERR_ARG;
+    jade_host::linear_crop(fs, bins, fmin, fmax, *k_lo, *k_hi);
+    return JADE_OK;
+}
+
+int jade_log_rows(float fs, int fft_size, int rows, float fmin, float fmax, int32_t* lo, int32_t* hi)
+{
+    if (!lo || !hi || rows < 1 || fft_size < 2 || fs <= 0.f) return JADE_ERR_ARG;
+    std::vector<int32_t> a, b;
+    jade_host::log_rows(fs, fft_size, rows, fmin, fmax, a, b);
+    memcpy(lo, a.data(), (size_t)rows * 4);
+    memcpy(hi, b.data(), (size_t)rows * 4);
+    return JADE_OK;
+}
+
+// ---- streaming ----------------------------------------------------------------------------------------
+int jade_push_samples(jade_engine* e, const float* const* planar, int nch, int nsamples)
+{
+    if (!e || !planar) return fail(e, JADE_ERR_ARG, "null argument");
+    if (!e->configured) return fail(e, JADE_ERR_STATE, "engine not configured");
+    const jade_config& c = e->cfg;
+    if (nch != c.channels) return fail(e, JADE_ERR_ARG, "got %d channels, configured %d", nch, c.channels);
+    if (nsamples < 0 || nsamples > c.max_push) return fail(e, JADE_ERR_ARG, "nsamples %d exceeds max_push %d", nsamples, c.max_push);
+    if (nsamples == 0) return JADE_OK;
+    std::lock_guard<std::mutex> lk(e->mu);
+    CU(e, cudaSetDevice(e->device));
+
+    // stage into a pinned, device-mapped slot (the kernel reads it over PCIe: no memcpy call on this path)
+    const int slot = e->stage_slot;
+    e->stage_slot = (slot + 1) % kStageSlots;
+    CU(e, cudaEventSynchronize(e->stage_ev[slot])); // normally long complete
+    float* hs = (float*)((char*)e->h_stage.p + (size_t)slot * e->stage_slot_bytes);
+    for (int ch = 0; ch < nch; ++ch) memcpy(hs + (size_t)ch * nsamples, planar[ch], (size_t)nsamples * 4);
+
+    // slide the linear history when it would overflow
+    long long slide_from = 0;
+    int keep = 0;
+    if (e->hist_fill + nsamples > e->hist_cap) {
+        const long long next_start = frame_start_abs(c, e->frames_done); // oldest sample still needed
+        long long from = next_start - e->hist_base_abs;
+        if (from < 0) from = 0;
+        from &= ~1LL; // keep frame starts even relative to the buffer
+        keep = (int)(e->hist_fill - from);
+        slide_from = from;
+        e->hist_base_abs += from;
+        e->hist_fill = keep;
+    }
+    const long long write_pos = e->hist_fill;
+    {
+        float* hist = (float*)e->d_hist.p;
+        long long cs = e->hist_cap;
+        int chn = nch, n = nsamples;
+        const float* stage = hs;
+        void* args[] = {&hist, &cs, &chn, &stage, &n, (void*)&write_pos, &slide_from, &keep};
+        const int blocks = std::max(1, std::min(32, (std::max(n, keep) + 255) / 256));
+        CU(e, cudaLaunchKernel((const void*)jade::ingest_kernel, dim3(blocks), dim3(256), args, 0, e->stream));
+        e->launches++;
+        CU(e, cudaEventRecord(e->stage_ev[slot], e->stream));
+    }
+    e->hist_fill += nsamples;
+    e->pushed += nsamples;
+
+    // Frames that became computable.  The reference always computes them; while paused it only skips the ring
+    // write and the counters (Spectrogram.cpp:111-118) -- nothing observable is left, so the launch is skipped.
+    const long long avail = columns_available(c, e->pushed);
+    if (avail > e->frames_done) {
+        if (!e->paused) {
+            long long j0 = e->frames_done, n = avail - e->frames_done, skip = 0;
+            if (n > e->W) { // more than a ring in one push: only the newest W survive
+                skip = n - e->W;
+                j0 += skip;
+                n = e->W;
+            }
+            KParams P;
+            fill_params(e, P);
+            P.samples = (const float*)e->d_hist.p;
+            P.stream_stride = 0;
+            P.channel_stride = e->hist_cap;
+            P.nsamples = e->hist_fill;
+            P.sample_base = e->hist_base_abs;
+            P.aligned2 = ((e->hist_cap % 2) == 0 && (c.hop % 2) == 0 && (c.block_stride % 2) == 0 &&
+                          (c.preroll % 2) == 0 && (e->hist_base_abs % 2) == 0) ? 1 : 0;
+            P.first_col = j0;
+            P.ncols = (int)n;
+            P.nstreams = 1;
+            P.pix = (uint32_t*)e->h_pixring.p; // device-mapped pinned ring: columns land in host memory directly
+            P.db = (float*)e->d_dbring.p;
+            P.ring_w = e->W;
+            P.ring_col0 = e->emitted + skip;
+            if (int r = launch_stft(e, P, e->stream)) return r;
+            e->emitted += skip + n;
+        }
+        e->frames_done = avail;
+    }
+    CU(e, cudaEventRecord(e->last_push_ev, e->stream));
+    return JADE_OK;
+}
+
+int jade_fetch_columns(jade_engine* e, uint32_t* pixels, float* db, int max_cols, int* ncols, int64_t* first_col)
+{
+    if (!e || !ncols) return fail(e, JADE_ERR_ARG, "null argument");
+    if (!e->configured) return fail(e, JADE_ERR_STATE, "engine not configured");
+    *ncols = 0;
+    long long from, to;
+    {
+        std::lock_guard<std::mutex> lk(e->mu);
+        from = e->fetched;
+        to = e->emitted;
+        if (to - from > e->W) from = to - e->W;
+        if (max_cols >= 0 && to - from > max_cols) from = to - max_cols;
+        e->fetched = to;
+    }
+    if (first_col) *first_col = from;
+    if (to <= from) return JADE_OK;
+    CU(e, cudaSetDevice(e->device));
+    CU(e, cudaEventSynchronize(e->last_push_ev));
+    const int W = e->W, R = e->R, B = e->B;
+    const uint32_t* ring = (const uint32_t*)e->h_pixring.p;
+    for (long long j = from; j < to; ++j) {
+        const long long slot = j % W;
+        if (pixels) memcpy(pixels + (size_t)(j - from) * R, ring + (size_t)slot * R, (size_t)R * 4);
+    }
+    if (db) {
+        // contiguous runs of ring slots
+        long long j = from;
+        while (j < to) {
+            const long long slot = j % W;
+            const long long run = std::min<long long>(to - j, W - slot);
+            CU(e, cudaMemcpy(db + (size_t)(j - from) * B, (const float*)e->d_dbring.p + (size_t)slot * B,
+                             (size_t)run * B * 4, cudaMemcpyDeviceToHost));
+            j += run;
+        }
+    }
+    *ncols = (int)(to - from);
+    return JADE_OK;
+}
+
+int jade_ring_info(jade_engine* e, int* ring_columns, int* rows, int* bins, int64_t* total_columns)
+{
+    if (!e) return JADE_ERR_ARG;
+    if (!e->configured) return fail(e, JADE_ERR_STATE, "engine not configured");
+    if (ring_columns) *ring_columns = e->W;
+    if (rows) *rows = e->R;
+    if (bins) *bins = e->B;
+    if (total_columns) *total_columns = e->emitted;
+    return JADE_OK;
+}
+
+int jade_recolor_ring(jade_engine* e, uint32_t* pixels)
+{
+    if (!e || !pixels) return fail(e, JADE_ERR_ARG, "null argument");
+    if (!e->configured) return fail(e, JADE_ERR_STATE, "engine not configured");
+    if (e->pooled) return fail(e, JADE_ERR_ARG, "recolor needs a per-bin row map (identity / linear crop)");
+    std::lock_guard<std::mutex> lk(e->mu);
+    CU(e, cudaSetDevice(e->device));
+    KParams P;
+    fill_params(e, P);
+    P.pix = (uint32_t*)e->h_pixring.p;
+    const float* dbc = (const float*)e->d_dbring.p;
+    long long ncolumns = e->W;
+    void* args[] = {&P, &dbc, &ncolumns};
+    const int grid = (int)std::min<long long>(ncolumns, (long long)e->sm_count * 8);
+    CU(e, cudaLaunchKernel((const void*)jade::recolor_kernel, dim3(grid), dim3(256), args, 0, e->stream));
+    e->launches++;
+    CU(e, cudaStreamSynchronize(e->stream));
+    memcpy(pixels, e->h_pixring.p, (size_t)e->W * e->R * 4);
+    return JADE_OK;
+}
+
+int jade_read_ring_db(jade_engine* e, float* db)
+{
+    if (!e || !db) return fail(e, JADE_ERR_ARG, "null argument");
+    if (!e->configured) return fail(e, JADE_ERR_STATE, "engine not configured");
+    CU(e, cudaSetDevice(e->device));
+    CU(e, cudaEventSynchronize(e->last_push_ev));
+    CU(e, cudaMemcpy(db, e->d_dbring.p, (size_t)e->W * e->B * 4, cudaMemcpyDeviceToHost));
+    return JADE_OK;
+}
+
+// ---- batch --------------------------------------------------------------------------------------------
+int64_t jade_columns_for(jade_engine* e, int64_t nsamples)
+{
+    if (!e || !e->configured || nsamples < 0) return -1;
+    return columns_available(e->cfg, nsamples);
+}
+
+int jade_render_device(jade_engine* e, const float* d_samples, int nstreams, int64_t nsamples, int64_t stream_stride,
+                       int64_t channel_stride, int64_t first_col, int64_t ncols, uint32_t* d_pixels, float* d_db,
+                       void* cuda_stream)
+{
+    if (!e || !d_samples) return fail(e, JADE_ERR_ARG, "null argument");
+    if (!e->configured) return fail(e, JADE_ERR_STATE, "engine not configured");
+    if (nstreams < 0 || ncols < 0 || first_col < 0 || nsamples < 0) return fail(e, JADE_ERR_ARG, "negative size");
+    if (ncols > 0x7fffffffLL) return fail(e, JADE_ERR_ARG, "ncols too large for one launch");
+    CU(e, cudaSetDevice(e->device));
+    const jade_config& c = e->cfg;
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : e->stream;
+    KParams P;
+    fill_params(e, P);
+    P.samples = d_samples;
+    P.stream_stride = stream_stride;
+    P.channel_stride = channel_stride;
+    P.nsamples = nsamples;
+    P.sample_base = 0;
+    P.aligned2 = ((stream_stride % 2) == 0 && (channel_stride % 2) == 0 && (c.hop % 2) == 0 && (c.block_stride % 2) == 0 &&
+                  (c.preroll % 2) == 0 && ((uintptr_t)d_samples % 8) == 0) ? 1 : 0;
+    P.first_col = first_col;
+    P.ncols = (int)ncols;
+    P.nstreams = nstreams;
+    P.pix = d_pixels;
+    P.db = d_db;
+    P.pix_stream_stride = (long long)ncols * e->R;
+    P.db_stream_stride = (long long)ncols * e->B;
+    P.ring_w = 0;
+    CU(e, cudaEventRecord(e->ev_t0, st));
+    if (int r = launch_stft(e, P, st)) return r;
+    CU(e, cudaEventRecord(e->ev_t1, st));
+    e->timed = true;
+    return JADE_OK;
+}
+
+int jade_sync(jade_engine* e)
+{
+    if (!e) return JADE_ERR_ARG;
+    CU(e, cudaSetDevice(e->device));
+    CU(e, cudaStreamSynchronize(e->stream));
+    for (int i = 0; i < kPipe; ++i) CU(e, cudaStreamSynchronize(e->pipe_stream[i]));
+    return JADE_OK;
+}
+
+double jade_last_kernel_seconds(jade_engine* e)
+{
+    if (!e || !e->timed) return -1.0;
+    cudaSetDevice(e->device);
+    if (cudaEventSynchronize(e->ev_t1) != cudaSuccess) return -1.0;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, e->ev_t0, e->ev_t1) != cudaSuccess) return -1.0;
+    return ms * 1e-3;
+}
+
+// One pipelined pass: chunks of (stream group x column range); H2D, kernel and D2H of consecutive chunks overlap
+// on kPipe streams.  Pageable caller buffers are staged through pinned memory; pinned ones are DMA'd directly.
+int jade_render_batch(jade_engine* e, const float* samples, int nstreams, int64_t nsamples, int64_t first_col,
+                      int64_t ncols, uint32_t* pixels, float* db)
+{
+    if (!e || !samples || (!pixels && !db)) return fail(e, JADE_ERR_ARG, "null argument");
+    if (!e->configured) return fail(e, JADE_ERR_STATE, "engine not configured");
+    if (nstreams <= 0 || ncols <= 0) return JADE_OK;
+    CU(e, cudaSetDevice(e->device));
+    const jade_config& c = e->cfg;
+    const int C = c.channels, R = e->R, B = e->B, N = e->N;
+    auto pinned = [](const void* p) {
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        return a.type == cudaMemoryTypeHost;
+    };
+    const bool in_pinned = pinned(samples);
+    const bool pix_pinned = pixels && pinned(pixels);
+    const bool db_pinned = db && pinned(db);
+
+    // chunk shape
+    const size_t budget = (size_t)96 << 20; // bytes of output per chunk
+    const size_t col_bytes = (size_t)(pixels ? R * 4 : 0) + (size_t)(db ? B * 4 : 0);
+    long long cols_per_chunk = ncols, streams_per_chunk = 1;
+    if ((size_t)ncols * col_bytes > budget) {
+        cols_per_chunk = std::max<long long>(1, (long long)(budget / col_bytes));
+    } else {
+        streams_per_chunk = std::max<long long>(1, std::min<long long>(nstreams, (long long)(budget / ((size_t)ncols * col_bytes))));
+    }
+    int slot = 0;
+    bool used[kPipe] = {false, false, false};
+    struct Pending {
+        bool active = false;
+        uint32_t* dst_pix = nullptr;
+        float* dst_db = nullptr;
+        size_t pix_bytes = 0, db_bytes = 0;
+    } pend[kPipe];
+    auto drain = [&](int s) -> int {
+        if (!used[s]) return 0;
+        CU(e, cudaEventSynchronize(e->pipe_done[s]));
+        if (pend[s].active) {
+            if (pend[s].dst_pix) memcpy(pend[s].dst_pix, e->pipe_hpix[s].p, pend[s].pix_bytes);
+            if (pend[s].dst_db) memcpy(pend[s].dst_db, e->pipe_hdb[s].p, pend[s].db_bytes);
+            pend[s].active = false;
+        }
+        return 0;
+    };
+
+    for (long long s0 = 0; s0 < nstreams; s0 += streams_per_chunk) {
+        const int ns = (int)std::min<long long>(streams_per_chunk, nstreams - s0);
+        for (long long c0 = 0; c0 < ncols; c0 += cols_per_chunk) {
+            const long long nc = std::min<long long>(cols_per_chunk, ncols - c0);
+            if (int r = drain(slot)) return r;
+            cudaStream_t st = e->pipe_stream[slot];
+            // sample range needed by columns [first_col+c0, first_col+c0+nc)
+            long long a = frame_start_abs(c, first_col + c0), b = frame_start_abs(c, first_col + c0 + nc - 1) + N;
+            a = std::max<long long>(0, a) & ~1LL;
+            b = std::min<long long>(nsamples, b);
+            long long len = std::max<long long>(0, b - a);
+            const long long len_pad = (len + 1) & ~1LL;
+            const size_t in_bytes = (size_t)ns * C * len_pad * 4;
+            if (e->pipe_in[slot].ensure(std::max<size_t>(in_bytes, 16))) return fail(e, JADE_ERR_CUDA, "device input allocation failed");
+            if (len > 0) {
+                const float* src = samples + ((size_t)s0 * C) * nsamples + a;
+                if (in_pinned) {
+                    CU(e, cudaMemcpy2DAsync(e->pipe_in[slot].p, (size_t)len_pad * 4, src, (size_t)nsamples * 4, (size_t)len * 4,
+                                            (size_t)ns * C, cudaMemcpyHostToDevice, st));
+                } else {
+                    if (e->pipe_hin[slot].ensure(in_bytes)) return fail(e, JADE_ERR_CUDA, "pinned input allocation failed");
+                    float* h = (float*)e->pipe_hin[slot].p;
+                    for (long long r = 0; r < (long long)ns * C; ++r)
+                        memcpy(h + r * len_pad, src + r * nsamples, (size_t)len * 4);
+                    CU(e, cudaMemcpyAsync(e->pipe_in[slot].p, h, in_bytes, cudaMemcpyHostToDevice, st));
+                }
+            }
+            const size_t pix_bytes = pixels ? (size_t)ns * nc * R * 4 : 0, db_bytes = db ? (size_t)ns * nc * B * 4 : 0;
+            if (pixels && e->pipe_pix[slot].ensure(pix_bytes)) return fail(e, JADE_ERR_CUDA, "device pixel allocation failed");
+            if (db && e->pipe_db[slot].ensure(db_bytes)) return fail(e, JADE_ERR_CUDA, "device dB allocation failed");
+            KParams P;
+            fill_params(e, P);
+            P.samples = (const float*)e->pipe_in[slot].p;
+            P.stream_stride = (long long)C * len_pad;
+            P.channel_stride = len_pad;
+            P.nsamples = len;
+            P.sample_base = a;
+            P.aligned2 = ((c.hop % 2) == 0 && (c.block_stride % 2) == 0 && (c.preroll % 2) == 0) ? 1 : 0;
+            P.first_col = first_col + c0;
+            P.ncols = (int)nc;
+            P.nstreams = ns;
+            P.pix = pixels ? (uint32_t*)e->pipe_pix[slot].p : nullptr;
+            P.db = db ? (float*)e->pipe_db[slot].p : nullptr;
+            P.pix_stream_stride = nc * R;
+            P.db_stream_stride = nc * B;
+            if (int r = launch_stft(e, P, st)) return r;
+            // outputs: the chunk is [ns][nc][R]; destination is [nstreams][ncols][R]
+            const bool contiguous = (nc == ncols);
+            if (pixels) {
+                uint32_t* dst = pixels + ((size_t)s0 * ncols + c0) * R;
+                if (pix_pinned) {
+                    if (contiguous) CU(e, cudaMemcpyAsync(dst, e->pipe_pix[slot].p, pix_bytes, cudaMemcpyDeviceToHost, st));
+                    else CU(e, cudaMemcpy2DAsync(dst, (size_t)ncols * R * 4, e->pipe_pix[slot].p, (size_t)nc * R * 4,
+                                                 (size_t)nc * R * 4, ns, cudaMemcpyDeviceToHost, st));
+                } else {
+                    if (e->pipe_hpix[slot].ensure(pix_bytes)) return fail(e, JADE_ERR_CUDA, "pinned pixel allocation failed");
+                    CU(e, cudaMemcpyAsync(e->pipe_hpix[slot].p, e->pipe_pix[slot].p, pix_bytes, cudaMemcpyDeviceToHost, st));
+                }
+            }
+            if (db) {
+                float* dst = db + ((size_t)s0 * ncols + c0) * B;
+                if (db_pinned) {
+                    if (contiguous) CU(e, cudaMemcpyAsync(dst, e->pipe_db[slot].p, db_bytes, cudaMemcpyDeviceToHost, st));
+                    else CU(e, cudaMemcpy2DAsync(dst, (size_t)ncols * B * 4, e->pipe_db[slot].p, (size_t)nc * B * 4,
+                                                 (size_t)nc * B * 4, ns, cudaMemcpyDeviceToHost, st));
+                } else {
+                    if (e->pipe_hdb[slot].ensure(db_bytes)) return fail(e, JADE_ERR_CUDA, "pinned dB allocation failed");
+                    CU(e, cudaMemcpyAsync(e->pipe_hdb[slot].p, e->pipe_db[slot].p, db_bytes, cudaMemcpyDeviceToHost, st));
+                }
+            }
+            CU(e, cudaEventRecord(e->pipe_done[slot], st));
+            used[slot] = true;
+            // pageable destinations need a host-side scatter after the chunk completes (only contiguous chunks or ns == 1)
+            if ((pixels && !pix_pinned) || (db && !db_pinned)) {
+                if (!contiguous && ns > 1) return fail(e, JADE_ERR_STATE, "internal: strided pageable chunk");
+                pend[slot].active = true;
+                pend[slot].dst_pix = (pixels && !pix_pinned) ? pixels + ((size_t)s0 * ncols + c0) * R : nullptr;
+                pend[slot].dst_db = (db && !db_pinned) ? db + ((size_t)s0 * ncols + c0) * B : nullptr;
+                pend[slot].pix_bytes = pix_bytes;
+                pend[slot].db_bytes = db_bytes;
+            }
+            slot = (slot + 1) % kPipe;
+        }
+    }
+    for (int s = 0; s < kPipe; ++s)
+        if (int r = drain(s)) return r;
+    return JADE_OK;
+}
+
+int jade_render_batch_multi(jade_engine* const* engines, int nengines, const float* samples, int nstreams,
+                            int64_t nsamples, int64_t first_col, int64_t ncols, uint32_t* pixels, float* db)
+{
+    if (!engines || nengines < 1) return fail(nullptr, JADE_ERR_ARG, "no engines");
+    if (nengines == 1) return jade_render_batch(engines[0], samples, nstreams, nsamples, first_col, ncols, pixels, db);
+    std::vector<std::thread> th;
+    std::vector<int> rc(nengines, 0);
+    for (int g = 0; g < nengines; ++g) {
+        th.emplace_back([&, g]() {
+            jade_engine* e = engines[g];
+            if (!e || !e->configured) {
+                rc[g] = JADE_ERR_STATE;
+                return;
+            }
+            const int C = e->cfg.channels, R = e->R, B = e->B;
+            if (nstreams >= nengines) { // range-partition the streams
+                const long long s0 = (long long)nstreams * g / nengines, s1 = (long long)nstreams * (g + 1) / nengines;
+                if (s1 > s0)
+                    rc[g] = jade_render_batch(e, samples + (size_t)s0 * C * nsamples, (int)(s1 - s0), nsamples, first_col, ncols,
+                                              pixels ? pixels + (size_t)s0 * ncols * R : nullptr,
+                                              db ? db + (size_t)s0 * ncols * B : nullptr);
+            } else if (nstreams == 1) { // range-partition the columns; the N-hop input halo is re-read, not exchanged
+                const long long c0 = ncols * g / nengines, c1 = ncols * (g + 1) / nengines;
+                if (c1 > c0)
+                    rc[g] = jade_render_batch(e, samples, 1, nsamples, first_col + c0, c1 - c0,
+                                              pixels ? pixels + (size_t)c0 * R : nullptr, db ? db + (size_t)c0 * B : nullptr);
+            } else {
+                if (g < nstreams)
+                    rc[g] = jade_render_batch(e, samples + (size_t)g * C * nsamples, 1, nsamples, first_col, ncols,
+                                              pixels ? pixels + (size_t)g * ncols * R : nullptr,
+                                              db ? db + (size_t)g * ncols * B : nullptr);
+            }
+        });
+    }
+    for (auto& t : th) t.join();
+    for (int g = 0; g < nengines; ++g)
+        if (rc[g]) return rc[g];
+    return JADE_OK;
+}
+
+int jade_synth_device(jade_engine* e, float* d_out, int nstreams, int channels, int64_t nsamples, int64_t stream_stride,
+                      int64_t channel_stride, int kind, uint64_t seed, void* cuda_stream)
+{
+    if (!e || !d_out) return fail(e, JADE_ERR_ARG, "null argument");
+    CU(e, cudaSetDevice(e->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : e->stream;
+    long long ss = stream_stride, cs = channel_stride, n = nsamples;
+    unsigned long long sd = seed;
+    float fs = e->configured ? e->cfg.sample_rate : 48000.f;
+    void* args[] = {&d_out, &ss, &cs, &nstreams, &channels, &n, &kind, &sd, &fs};
+    CU(e, cudaLaunchKernel((const void*)jade::synth_kernel, dim3(e->sm_count * 8), dim3(256), args, 0, st));
+    e->launches++;
+    return JADE_OK;
+}
+
+void* jade_host_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
+        fail(nullptr, JADE_ERR_CUDA, "cudaHostAlloc(%zu) failed", bytes);
+        return nullptr;
+    }
+    return p;
+}
+int jade_host_free(void* p)
+{
+    if (p && cudaFreeHost(p) != cudaSuccess) return fail(nullptr, JADE_ERR_CUDA, "cudaFreeHost failed");
+    return JADE_OK;
+}
+
+int64_t jade_kernel_launches(jade_engine* e) { return e ? (int64_t)e->launches.load() : 0; }
+const char* jade_kernel_name(jade_engine* e) { return (e && e->configured) ? e->kc.name : ""; }
+
+} // extern "C"

@@ -1,0 +1,663 @@
+// jade_kernels.cuh -- fused STFT -> power -> channel mix -> dB -> row map -> palette kernels for sm_100a.
+//
+// One launch covers the whole hot path of the reference (file:line relative to /root/reference):
+//   framing            Spectrogram.cpp:50-56      (frame start computed per column, no copy pass)
+//   window multiply    Spectrogram.cpp:137-141    (fused into the load)
+//   real FFT -> power  Spectrogram.cpp:144        (spectrum::power, external; written from scratch here)
+//   channel mix        Spectrogram.cpp:64-106
+//   10*log10(p+1e-11)  Spectrogram.cpp:36,107
+//   bin -> row (flip)  Spectrogram.cpp:642        (+ linear crop :441-459, + log max-pool extension)
+//   getRGBColor | 0xFF000000   CColorpalette.h:32-47, Spectrogram.cpp:636-637
+//
+// Kernel families
+//   stft_warp_kernel<T>   N = 64*T <= 2048   : one FFT per T lanes, 32 complex values per thread in registers,
+//                                              two radix passes (32 x T) with one shared-memory transpose per warp.
+//   stft_cta_kernel<R1>   N = 2048*R1 <= 32768: CTA of R1 warps; radix-R1 column pass, then one 1024-point row FFT
+//                                              per warp (same register code), rows staged in shared memory.
+//   (N = 65536 is built from two half-size real FFTs, see stft_cta2_kernel.)
+//
+// The real-input FFT packs z[m] = x[2m] + i x[2m+1] (M = N/2 complex points) and finishes with the split
+//   X[k] = (Z[k] + conj Z[M-k]) - i W_N^k (Z[k] - conj Z[M-k])      (window table is pre-multiplied by 1/2)
+//
+// All code here also compiles for the host SIMT emulator in tests/emu (JADE_EMU) -- test infrastructure only.
+#pragma once
+#include <stdint.h>
+
+#include "jade_fft_regs.cuh"
+
+#if defined(JADE_EMU)
+#include "cuda_emu.h"
+#define JADE_KERNEL(...) inline void
+#define JADE_DYN_SMEM(name) float4* name = reinterpret_cast<float4*>(jade_emu::dyn_smem())
+#define JADE_RESTRICT
+#define JADE_LOG2F(x) ::log2f(x)
+#define JADE_FDIV(a, b) ((a) / (b))
+#else
+#define JADE_KERNEL(...) __global__ void __launch_bounds__(__VA_ARGS__)
+#define JADE_DYN_SMEM(name) extern __shared__ float4 name[]
+#define JADE_RESTRICT __restrict__
+#define JADE_LOG2F(x) __log2f(x)
+#define JADE_FDIV(a, b) __fdiv_rn((a), (b))
+#endif
+
+namespace jade {
+
+enum { K_MIX_ABSMEAN = 0, K_MIX_MAX = 1, K_MIX_MIN = 2, K_MIX_LEFT = 3, K_MIX_RIGHT = 4 };
+
+struct i2 {
+    int lo, hi;
+};
+
+struct KParams {
+    // ---- input samples (device), planar: samples[stream*stream_stride + channel*channel_stride + i]
+    const float* samples;
+    long long stream_stride;
+    long long channel_stride;
+    long long nsamples;     // valid samples per channel; reads outside [0,nsamples) give 0
+    long long sample_base;  // absolute sample index of samples[..][0]
+    int aligned2;           // every frame start is even and the channel bases are 8-byte aligned
+    // ---- geometry: column j starts at (j / fb) * bstride + (j % fb) * hop - preroll   (absolute sample index)
+    int N, M, B;
+    int hop, fb, bstride, preroll;
+    long long first_col;
+    int ncols;              // columns per stream in this launch
+    int nstreams;
+    int channels;
+    int mix_mode;
+    // ---- tables (device)
+    const float* window;    // N floats, already multiplied by 0.5*sqrt(power_scale)
+    const cpx* twI;         // [32][T]   W_{32T}^{k1*s}       (warp FFT inter-pass twiddles; T=32 for row FFTs)
+    const cpx* twP;         // [M+1]     W_N^k                (real-FFT split)
+    const cpx* twA;         // [R1][1024] W_M^{k1*n2}         (CTA kernels: column-pass twiddles)
+    const uint32_t* palette; // npal entries, alpha / byte order already baked in
+    int npal;
+    float pmin, pmax, pmaxc, pmult; // CColorPalette m_Min, m_Max, m_Max*0.9999f, m_AccessMult
+    int db_precise;         // 1: float(10.0*log10(double(p+1e-11f))) exactly as the reference; 0: MUFU log2
+    // ---- rows
+    int pooled;             // 0: rows are bins [k_lo,k_hi); 1: row r = max over bins [row_bins[r].lo, row_bins[r].hi)
+    int R;                  // rows per column
+    int k_lo, k_hi;
+    int flip;               // 1: row 0 is the highest frequency (reference orientation, Spectrogram.cpp:642)
+    const i2* row_bins;     // [R] (pooled only)
+    // ---- outputs (device)
+    uint32_t* pix;          // [stream][col][R]   (may be null)
+    float* db;              // [stream][col][B]   (may be null)
+    long long pix_stream_stride; // in elements
+    long long db_stream_stride;
+    int ring_w;             // >0: column slot = (ring_col0 + j - first_col) % ring_w (streaming ring); 0: j - first_col
+    long long ring_col0;    // ring column counter of the first column of this launch
+    // ---- scratch for the two-half kernels (N = 65536)
+    cpx* scratch_e;         // [grid][M/2+1] complex
+    float* scratch_p;       // [grid][B] floats
+    const cpx* twH;         // [M/2+1]  W_{N/2}^k  (split of the half-size real FFTs)
+};
+
+JADE_DEVICE float to_db(float p, int precise)
+{
+    const float sh = p + 1e-11f; // Spectrogram.cpp:36,107
+    if (precise) return (float)(10.0 * log10((double)sh));
+    return 3.01029995663981195f * JADE_LOG2F(sh);
+}
+
+// CColorPalette::getRGBColor (CColorpalette.h:32-47) on the baked table.  The index is additionally clamped at 0
+// (the reference would read out of bounds when m_Min > m_Max).
+JADE_DEVICE uint32_t colour_of(float v, const KParams& P, const uint32_t* pal)
+{
+    if (v >= P.pmax) v = P.pmaxc;
+    if (v < P.pmin) v = P.pmin;
+    const float d = v - P.pmin;
+    int idx = (int)(d * P.pmult);
+    idx = idx < P.npal ? idx : P.npal - 1;
+    idx = idx < 0 ? 0 : idx;
+    return pal[idx];
+}
+
+JADE_DEVICE cpx load_pair(const float* JADE_RESTRICT x, long long idx, long long ns, bool fast)
+{
+    if (fast) {
+        const cpx* p = reinterpret_cast<const cpx*>(x + idx);
+        return *p;
+    }
+    cpx r;
+    r.x = (idx >= 0 && idx < ns) ? x[idx] : 0.f;
+    r.y = (idx + 1 >= 0 && idx + 1 < ns) ? x[idx + 1] : 0.f;
+    return r;
+}
+
+// |X'[k]|^2 from Z[k], Z[M-k] and W_N^k (see header comment)
+JADE_DEVICE float split_power(cpx zk, cpx zp, cpx w)
+{
+    const float ax = zk.x + zp.x, ay = zk.y - zp.y;
+    const float bx = zk.x - zp.x, by = zk.y + zp.y;
+    const float xr = ax + fm(w.x, by, w.y * bx);
+    const float xi = ay - fm(w.x, bx, -(w.y * by));
+    return fm(xr, xr, xi * xi);
+}
+JADE_DEVICE cpx split_value(cpx zk, cpx zp, cpx w)
+{
+    const float ax = zk.x + zp.x, ay = zk.y - zp.y;
+    const float bx = zk.x - zp.x, by = zk.y + zp.y;
+    return mk(ax + fm(w.x, by, w.y * bx), ay - fm(w.x, bx, -(w.y * by)));
+}
+
+JADE_DEVICE void mix_init(float& a, int mode) { a = (mode == K_MIX_MIN) ? 1000000.0f : 0.0f; }
+JADE_DEVICE void mix_add(float& a, float p, int mode, int ch, int right_ch)
+{
+    switch (mode) {
+    case K_MIX_ABSMEAN: a += p; break;
+    case K_MIX_MAX: if (p > a) a = p; break;
+    case K_MIX_MIN: if (p < a) a = p; break;
+    case K_MIX_LEFT: if (ch == 0) a = p; break;
+    default: if (ch == right_ch) a = p; break;
+    }
+}
+JADE_DEVICE float mix_done(float a, int mode, float nch) { return mode == K_MIX_ABSMEAN ? JADE_FDIV(a, nch) : a; }
+
+struct ColOut {
+    uint32_t* pix; // column base or null
+    float* db;     // column base or null
+};
+JADE_DEVICE ColOut col_out(const KParams& P, int stream, long long j)
+{
+    const long long slot = P.ring_w > 0 ? ((P.ring_col0 + (j - P.first_col)) % P.ring_w) : (j - P.first_col);
+    ColOut o;
+    o.pix = P.pix ? P.pix + stream * P.pix_stream_stride + slot * P.R : nullptr;
+    o.db = P.db ? P.db + stream * P.db_stream_stride + slot * P.B : nullptr;
+    return o;
+}
+JADE_DEVICE long long frame_start(const KParams& P, long long j)
+{
+    return (j / P.fb) * (long long)P.bstride + (j % P.fb) * (long long)P.hop - P.preroll - P.sample_base;
+}
+
+// dB + pixel for one bin of the un-pooled row map
+JADE_DEVICE void emit_bin(const KParams& P, const uint32_t* pal, const ColOut& o, int k, float power)
+{
+    const float d = to_db(power, P.db_precise);
+    if (o.db) o.db[k] = d;
+    if (o.pix && k >= P.k_lo && k < P.k_hi) {
+        const int row = P.flip ? (P.k_hi - 1 - k) : (k - P.k_lo);
+        o.pix[row] = colour_of(d, P, pal);
+    }
+}
+// pooled rows from a power spectrum (shared or global memory); threads tid..step
+JADE_DEVICE void emit_pooled(const KParams& P, const uint32_t* pal, const ColOut& o, const float* spec, int tid, int step)
+{
+    if (!o.pix) return;
+    for (int r = tid; r < P.R; r += step) {
+        const i2 rb = P.row_bins[r];
+        float mx = spec[rb.lo];
+        for (int k = rb.lo + 1; k < rb.hi; ++k) mx = fmaxf(mx, spec[k]);
+        const float d = to_db(mx, P.db_precise);
+        o.pix[P.flip ? (P.R - 1 - r) : r] = colour_of(d, P, pal);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Warp-level M = 32*T point complex FFT, T lanes per transform (F = 32/T transforms per warp).
+// in : v[brev5(n1)] = z[s + T*n1]           (s = lane % T)
+// out: u[i*T + k2]  = Z[(s + T*i) + 32*k2]  (i < 32/T, k2 < T)  i.e. bin k = s + T*q sits in u[(q % F)*T + q / F]
+// xw : this transform's shared-memory scratch (M complex words); synchronised with __syncwarp only.
+// ---------------------------------------------------------------------------------------------------------
+template <int T>
+JADE_DEVICE void warp_fft(cpx* v, cpx* u, cpx* xw, const cpx* twI, int s)
+{
+    constexpr int F = 32 / T;
+    fft_dit<32>(v);
+#pragma unroll
+    for (int k1 = 0; k1 < 32; ++k1) {
+        const cpx t = (k1 == 0) ? v[0] : cmul(v[k1], twI[k1 * T + s]);
+        xw[k1 * T + (s ^ (k1 & (T - 1)))] = t;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < F; ++i) {
+        const int k1 = s + T * i;
+#pragma unroll
+        for (int jx = 0; jx < T; ++jx) u[i * T + brev(jx, ilog2c(T))] = xw[k1 * T + (jx ^ s)];
+        fft_dit<T>(u + i * T);
+    }
+    __syncwarp();
+}
+
+// =========================================================================================================
+// Class A: N = 64*T
+// =========================================================================================================
+constexpr int WARP_KERNEL_WARPS = 8;
+
+template <int T>
+struct WarpCfg {
+    static constexpr int M = 32 * T;
+    static constexpr int N = 2 * M;
+    static constexpr int B = M + 1;
+    static constexpr int F = 32 / T;
+    static constexpr int FS = M + (T < 16 ? T : 0);      // per-transform stride in the exchange buffer (complex words)
+    static constexpr int SPEC_STRIDE = ((B + 3) / 4) * 4; // floats
+    // shared memory layout in bytes
+    static constexpr int off_twI = 0;
+    static constexpr int off_win = off_twI + 32 * T * 8;
+    static constexpr int off_twP = off_win + M * 8;
+    static constexpr int off_pal = off_twP + ((M + 1) * 8 + 15) / 16 * 16;
+    static JADE_HD int off_xch(int npal) { return off_pal + (npal * 4 + 15) / 16 * 16; }
+    static JADE_HD int smem_bytes(int npal, bool pooled)
+    {
+        return off_xch(npal) + WARP_KERNEL_WARPS * F * FS * 8 + (pooled ? WARP_KERNEL_WARPS * F * SPEC_STRIDE * 4 : 0);
+    }
+};
+
+template <int T, bool MULTI, bool POOL>
+JADE_KERNEL(WARP_KERNEL_WARPS * 32) stft_warp_kernel(const KParams P)
+{
+    using Cfg = WarpCfg<T>;
+    constexpr int M = Cfg::M, N = Cfg::N, F = Cfg::F, FS = Cfg::FS;
+    JADE_DYN_SMEM(smem);
+    char* sm = reinterpret_cast<char*>(smem);
+    cpx* s_twI = reinterpret_cast<cpx*>(sm + Cfg::off_twI);
+    cpx* s_win = reinterpret_cast<cpx*>(sm + Cfg::off_win);
+    cpx* s_twP = reinterpret_cast<cpx*>(sm + Cfg::off_twP);
+    uint32_t* s_pal = reinterpret_cast<uint32_t*>(sm + Cfg::off_pal);
+    cpx* s_xch = reinterpret_cast<cpx*>(sm + Cfg::off_xch(P.npal));
+    float* s_spec = reinterpret_cast<float*>(s_xch + WARP_KERNEL_WARPS * F * FS);
+
+    for (int i = threadIdx.x; i < 32 * T; i += blockDim.x) s_twI[i] = P.twI[i];
+    for (int i = threadIdx.x; i < M; i += blockDim.x) s_win[i] = mk(P.window[2 * i], P.window[2 * i + 1]);
+    for (int i = threadIdx.x; i <= M; i += blockDim.x) s_twP[i] = P.twP[i];
+    for (int i = threadIdx.x; i < P.npal; i += blockDim.x) s_pal[i] = P.palette[i];
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int f = lane / T, s = lane % T;
+    cpx* xw = s_xch + (warp * F + f) * FS;
+    float* spec = s_spec + (warp * F + f) * Cfg::SPEC_STRIDE;
+
+    const long long groups = (P.ncols + F - 1) / F;
+    const long long total = groups * P.nstreams;
+    const int right_ch = P.channels > 1 ? 1 : 0;
+    const float nchf = (float)P.channels;
+
+    for (long long g = (long long)blockIdx.x * WARP_KERNEL_WARPS + warp; g < total;
+         g += (long long)gridDim.x * WARP_KERNEL_WARPS) {
+        const int stream = (int)(g / groups);
+        long long jrel = (g % groups) * F + f;
+        const bool active = jrel < P.ncols;
+        if (!active) jrel = P.ncols - 1;
+        const long long j = P.first_col + jrel;
+        const long long st = frame_start(P, j);
+        const bool fast = P.aligned2 && st >= 0 && st + N <= P.nsamples;
+
+        float acc[33];
+        if (MULTI) {
+#pragma unroll
+            for (int q = 0; q < 33; ++q) mix_init(acc[q], P.mix_mode);
+        }
+        // Left / Right need a single channel only
+        int ch0 = 0, ch1 = P.channels;
+        if (MULTI && P.mix_mode == K_MIX_LEFT) ch1 = 1;
+        if (MULTI && P.mix_mode == K_MIX_RIGHT) { ch0 = right_ch; ch1 = right_ch + 1; }
+
+        for (int ch = ch0; ch < ch1; ++ch) {
+            const float* x = P.samples + stream * P.stream_stride + ch * P.channel_stride;
+            cpx v[32], u[32];
+#pragma unroll
+            for (int n1 = 0; n1 < 32; ++n1) {
+                const int m = s + T * n1;
+                const cpx z = load_pair(x, st + 2 * m, P.nsamples, fast);
+                const cpx w = s_win[m];
+                v[brev(n1, 5)] = mk(z.x * w.x, z.y * w.y);
+            }
+            warp_fft<T>(v, u, xw, s_twI, s);
+            // natural-order copy of Z for the partner reads of the split
+#pragma unroll
+            for (int i = 0; i < F; ++i)
+#pragma unroll
+                for (int k2 = 0; k2 < T; ++k2) xw[(s + T * i) + 32 * k2] = u[i * T + k2];
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 32; ++q) {
+                const int k = s + T * q;
+                const cpx zk = u[(q % F) * T + q / F];
+                const cpx zp = xw[(M - k) & (M - 1)];
+                const float p = split_power(zk, zp, s_twP[k]);
+                if (MULTI) mix_add(acc[q], p, P.mix_mode, ch, right_ch);
+                else acc[q] = p;
+            }
+            {   // Nyquist bin k = M (kept by sub-lane 0; computed by all lanes to stay convergent)
+                const cpx z0 = xw[0];
+                const float p = split_power(z0, z0, s_twP[M]);
+                if (MULTI) mix_add(acc[32], p, P.mix_mode, ch, right_ch);
+                else acc[32] = p;
+            }
+            __syncwarp();
+        }
+        if (MULTI) {
+#pragma unroll
+            for (int q = 0; q < 33; ++q) acc[q] = mix_done(acc[q], P.mix_mode, nchf);
+        }
+        const ColOut o = active ? col_out(P, stream, j) : ColOut{nullptr, nullptr};
+        if (!POOL) {
+#pragma unroll
+            for (int q = 0; q < 32; ++q) emit_bin(P, s_pal, o, s + T * q, acc[q]);
+            if (s == 0) emit_bin(P, s_pal, o, M, acc[32]);
+        } else {
+#pragma unroll
+            for (int q = 0; q < 32; ++q) {
+                spec[s + T * q] = acc[q];
+                if (o.db) o.db[s + T * q] = to_db(acc[q], P.db_precise);
+            }
+            if (s == 0) {
+                spec[M] = acc[32];
+                if (o.db) o.db[M] = to_db(acc[32], P.db_precise);
+            }
+            __syncwarp();
+            emit_pooled(P, s_pal, o, spec, s, T);
+            __syncwarp();
+        }
+    }
+}
+
+// =========================================================================================================
+// Class B: N = 2048*R1, one frame per CTA iteration, CTA = R1 warps
+// =========================================================================================================
+template <int R1>
+struct CtaCfg {
+    static constexpr int M = 1024 * R1;
+    static constexpr int N = 2 * M;
+    static constexpr int B = M + 1;
+    static constexpr int THREADS = 32 * R1;
+    static constexpr int RS = 1024 + 16 / R1; // row stride (complex words)
+    static constexpr int off_row = 0;
+    static constexpr int off_twI = off_row + R1 * RS * 8;
+    static constexpr int off_pal = off_twI + 1024 * 8;
+    static JADE_HD int off_spec(int npal) { return off_pal + (npal * 4 + 15) / 16 * 16; }
+    static JADE_HD int smem_bytes(int npal, bool pooled) { return off_spec(npal) + (pooled ? ((B + 3) / 4) * 16 : 0); }
+};
+
+// Z[k] of the M-point transform inside the row buffer (k1 = k % R1 is the row, k / R1 the row-FFT bin)
+template <int R1>
+JADE_DEVICE cpx rowbuf_get(const cpx* rowbuf, int k)
+{
+    return rowbuf[(k & (R1 - 1)) * CtaCfg<R1>::RS + (k / R1)];
+}
+
+// M = 1024*R1 point complex FFT of z[m] = ld(m) by the whole CTA; result left in rowbuf (see rowbuf_get).
+template <int R1, typename Loader>
+JADE_DEVICE void cta_fft(cpx* rowbuf, const cpx* s_twI, const cpx* JADE_RESTRICT twA, Loader ld)
+{
+    using Cfg = CtaCfg<R1>;
+    constexpr int RS = Cfg::RS, CPT = 32 / R1;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    // column pass: radix R1 over n1, thread owns columns n2 = t + THREADS*c
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) {
+        const int n2 = t + Cfg::THREADS * c;
+        cpx a[R1];
+#pragma unroll
+        for (int n1 = 0; n1 < R1; ++n1) a[brev(n1, ilog2c(R1))] = ld(n2 + 1024 * n1);
+        fft_dit<R1>(a);
+#pragma unroll
+        for (int k1 = 0; k1 < R1; ++k1) rowbuf[k1 * RS + n2] = (k1 == 0) ? a[0] : cmul(a[k1], twA[k1 * 1024 + n2]);
+    }
+    __syncthreads();
+    // row pass: warp `warp` transforms row k1 = warp (1024 points) in place
+    cpx* row = rowbuf + warp * RS;
+    cpx v[32], u[32];
+#pragma unroll
+    for (int n1 = 0; n1 < 32; ++n1) v[brev(n1, 5)] = row[lane + 32 * n1];
+    __syncwarp();
+    warp_fft<32>(v, u, row, s_twI, lane);
+#pragma unroll
+    for (int k2 = 0; k2 < 32; ++k2) row[lane + 32 * k2] = u[k2];
+    __syncthreads();
+}
+
+template <int R1, bool MULTI, bool POOL>
+JADE_KERNEL(32 * R1) stft_cta_kernel(const KParams P)
+{
+    using Cfg = CtaCfg<R1>;
+    constexpr int M = Cfg::M, N = Cfg::N, THREADS = Cfg::THREADS;
+    JADE_DYN_SMEM(smem);
+    char* sm = reinterpret_cast<char*>(smem);
+    cpx* rowbuf = reinterpret_cast<cpx*>(sm + Cfg::off_row);
+    cpx* s_twI = reinterpret_cast<cpx*>(sm + Cfg::off_twI);
+    uint32_t* s_pal = reinterpret_cast<uint32_t*>(sm + Cfg::off_pal);
+    float* spec = reinterpret_cast<float*>(sm + Cfg::off_spec(P.npal));
+
+    const int t = threadIdx.x;
+    for (int i = t; i < 1024; i += THREADS) s_twI[i] = P.twI[i];
+    for (int i = t; i < P.npal; i += THREADS) s_pal[i] = P.palette[i];
+    __syncthreads();
+
+    const long long total = (long long)P.ncols * P.nstreams;
+    const int right_ch = P.channels > 1 ? 1 : 0;
+    const float nchf = (float)P.channels;
+    const cpx* JADE_RESTRICT winp = reinterpret_cast<const cpx*>(P.window);
+
+    for (long long g = blockIdx.x; g < total; g += gridDim.x) {
+        const int stream = (int)(g / P.ncols);
+        const long long j = P.first_col + (g % P.ncols);
+        const long long st = frame_start(P, j);
+        const bool fast = P.aligned2 && st >= 0 && st + N <= P.nsamples;
+
+        float acc[33];
+        if (MULTI) {
+#pragma unroll
+            for (int q = 0; q < 33; ++q) mix_init(acc[q], P.mix_mode);
+        }
+        int ch0 = 0, ch1 = P.channels;
+        if (MULTI && P.mix_mode == K_MIX_LEFT) ch1 = 1;
+        if (MULTI && P.mix_mode == K_MIX_RIGHT) { ch0 = right_ch; ch1 = right_ch + 1; }
+
+        for (int ch = ch0; ch < ch1; ++ch) {
+            const float* x = P.samples + stream * P.stream_stride + ch * P.channel_stride;
+            const long long ns = P.nsamples;
+            cta_fft<R1>(rowbuf, s_twI, P.twA, [&](int m) {
+                const cpx z = load_pair(x, st + 2 * m, ns, fast);
+                const cpx w = winp[m];
+                return mk(z.x * w.x, z.y * w.y);
+            });
+#pragma unroll
+            for (int q = 0; q < 32; ++q) {
+                const int k = t + THREADS * q;
+                const cpx zk = rowbuf_get<R1>(rowbuf, k);
+                const cpx zp = rowbuf_get<R1>(rowbuf, (M - k) & (M - 1));
+                const float p = split_power(zk, zp, P.twP[k]);
+                if (MULTI) mix_add(acc[q], p, P.mix_mode, ch, right_ch);
+                else acc[q] = p;
+            }
+            {
+                const cpx z0 = rowbuf[0];
+                const float p = split_power(z0, z0, P.twP[M]);
+                if (MULTI) mix_add(acc[32], p, P.mix_mode, ch, right_ch);
+                else acc[32] = p;
+            }
+            __syncthreads();
+        }
+        if (MULTI) {
+#pragma unroll
+            for (int q = 0; q < 33; ++q) acc[q] = mix_done(acc[q], P.mix_mode, nchf);
+        }
+        const ColOut o = col_out(P, stream, j);
+        if (!POOL) {
+#pragma unroll
+            for (int q = 0; q < 32; ++q) emit_bin(P, s_pal, o, t + THREADS * q, acc[q]);
+            if (t == 0) emit_bin(P, s_pal, o, M, acc[32]);
+        } else {
+#pragma unroll
+            for (int q = 0; q < 32; ++q) {
+                spec[t + THREADS * q] = acc[q];
+                if (o.db) o.db[t + THREADS * q] = to_db(acc[q], P.db_precise);
+            }
+            if (t == 0) {
+                spec[M] = acc[32];
+                if (o.db) o.db[M] = to_db(acc[32], P.db_precise);
+            }
+            __syncthreads();
+            emit_pooled(P, s_pal, o, spec, t, THREADS);
+            __syncthreads();
+        }
+    }
+}
+
+// =========================================================================================================
+// Class C: N = 4096*R1 (R1 = 16 -> N = 65536) from two half-size real FFTs (decimation in time on the REAL data):
+//   X[k] = E[k] + W_N^k O[k],  X[N/2-k] = conj(E[k] - W_N^k O[k]),  k = 0..N/4
+// E / O = real FFT (size N/2, M2 = N/4 = 1024*R1 complex points) of the even / odd windowed samples.
+// The complex working set of one half (8*M2 bytes) fits in shared memory; E and the mixed power spectrum go
+// through an L2-resident per-CTA scratch slot.
+// =========================================================================================================
+template <int R1, bool MULTI>
+JADE_KERNEL(32 * R1) stft_cta2_kernel(const KParams P)
+{
+    using Cfg = CtaCfg<R1>;
+    constexpr int M2 = Cfg::M;      // complex points per half
+    constexpr int NH = 2 * M2;      // real points per half  (= N/2)
+    constexpr int N = 2 * NH;
+    constexpr int THREADS = Cfg::THREADS;
+    JADE_DYN_SMEM(smem);
+    char* sm = reinterpret_cast<char*>(smem);
+    cpx* rowbuf = reinterpret_cast<cpx*>(sm + Cfg::off_row);
+    cpx* s_twI = reinterpret_cast<cpx*>(sm + Cfg::off_twI);
+    uint32_t* s_pal = reinterpret_cast<uint32_t*>(sm + Cfg::off_pal);
+
+    const int t = threadIdx.x;
+    for (int i = t; i < 1024; i += THREADS) s_twI[i] = P.twI[i];
+    for (int i = t; i < P.npal; i += THREADS) s_pal[i] = P.palette[i];
+    __syncthreads();
+
+    cpx* se = P.scratch_e + (long long)blockIdx.x * (M2 + 1);
+    float* sp = P.scratch_p + (long long)blockIdx.x * (NH + 1);
+    const long long total = (long long)P.ncols * P.nstreams;
+    const int right_ch = P.channels > 1 ? 1 : 0;
+    const float nchf = (float)P.channels;
+
+    for (long long g = blockIdx.x; g < total; g += gridDim.x) {
+        const int stream = (int)(g / P.ncols);
+        const long long j = P.first_col + (g % P.ncols);
+        const long long st = frame_start(P, j);
+        const bool fast = st >= 0 && st + N <= P.nsamples;
+        int ch0 = 0, ch1 = P.channels;
+        if (MULTI && P.mix_mode == K_MIX_LEFT) ch1 = 1;
+        if (MULTI && P.mix_mode == K_MIX_RIGHT) { ch0 = right_ch; ch1 = right_ch + 1; }
+
+        for (int ch = ch0; ch < ch1; ++ch) {
+            const float* x = P.samples + stream * P.stream_stride + ch * P.channel_stride;
+            const long long ns = P.nsamples;
+            const float* JADE_RESTRICT win = P.window;
+            for (int half = 0; half < 2; ++half) {
+                // z[m] = xw[4m + half] + i xw[4m + 2 + half]
+                cta_fft<R1>(rowbuf, s_twI, P.twA, [&](int m) {
+                    const long long i0 = st + 4LL * m + half, i1 = i0 + 2;
+                    const float a = (fast || (i0 >= 0 && i0 < ns)) ? x[i0] : 0.f;
+                    const float b = (fast || (i1 >= 0 && i1 < ns)) ? x[i1] : 0.f;
+                    return mk(a * win[4 * m + half], b * win[4 * m + 2 + half]);
+                });
+                for (int k = t; k <= M2; k += THREADS) {
+                    const cpx zk = rowbuf_get<R1>(rowbuf, k & (M2 - 1));
+                    const cpx zp = rowbuf_get<R1>(rowbuf, (M2 - k) & (M2 - 1));
+                    const cpx hv = split_value(zk, zp, P.twH[k]); // E[k] or O[k]
+                    if (half == 0) {
+                        se[k] = hv;
+                    } else {
+                        const cpx e = se[k];
+                        const cpx q = cmul(hv, P.twP[k]);
+                        const float ar = e.x + q.x, ai = e.y + q.y, br = e.x - q.x, bi = e.y - q.y;
+                        const float p1 = fm(ar, ar, ai * ai), p2 = fm(br, br, bi * bi);
+                        const int k2 = NH - k;
+                        if (!MULTI) {
+                            sp[k] = p1;
+                            sp[k2] = p2;
+                        } else {
+                            float a1, a2;
+                            if (ch == ch0) { mix_init(a1, P.mix_mode); mix_init(a2, P.mix_mode); }
+                            else { a1 = sp[k]; a2 = sp[k2]; }
+                            mix_add(a1, p1, P.mix_mode, ch, right_ch);
+                            mix_add(a2, p2, P.mix_mode, ch, right_ch);
+                            sp[k] = a1;
+                            if (k2 != k) sp[k2] = a2;
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        const ColOut o = col_out(P, stream, j);
+        if (MULTI) {
+            for (int k = t; k <= NH; k += THREADS) sp[k] = mix_done(sp[k], P.mix_mode, nchf);
+            __syncthreads();
+        }
+        if (!P.pooled) {
+            for (int k = t; k <= NH; k += THREADS) emit_bin(P, s_pal, o, k, sp[k]);
+        } else {
+            if (o.db)
+                for (int k = t; k <= NH; k += THREADS) o.db[k] = to_db(sp[k], P.db_precise);
+            emit_pooled(P, s_pal, o, sp, t, THREADS);
+        }
+        __syncthreads();
+    }
+}
+
+// =========================================================================================================
+// Small helper kernels
+// =========================================================================================================
+// Re-colour stored dB columns (ring or batch) -- SpectrogramComponent's m_recomputeAll path (Spectrogram.cpp:623-657)
+JADE_KERNEL(256) recolor_kernel(const KParams P, const float* dbcols, long long ncolumns)
+{
+    for (long long c = blockIdx.x; c < ncolumns; c += gridDim.x) {
+        const float* d = dbcols + c * P.B;
+        uint32_t* o = P.pix + c * P.R;
+        for (int k = P.k_lo + threadIdx.x; k < P.k_hi; k += blockDim.x) {
+            const int row = P.flip ? (P.k_hi - 1 - k) : (k - P.k_lo);
+            o[row] = colour_of(d[k], P, P.palette);
+        }
+    }
+}
+
+// Append `n` staged samples per channel to the device history (streaming path).  If `slide` > 0 the last `keep`
+// samples are first moved to the front (source and destination ranges never overlap, see engine).
+JADE_KERNEL(256) ingest_kernel(float* hist, long long channel_stride, int channels, const float* stage, int n,
+                               long long write_pos, long long slide_from, int keep)
+{
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, step = gridDim.x * blockDim.x;
+    for (int ch = 0; ch < channels; ++ch) {
+        float* h = hist + ch * channel_stride;
+        if (keep > 0)
+            for (int i = tid; i < keep; i += step) h[i] = h[slide_from + i];
+        const float* s = stage + (long long)ch * n;
+        for (int i = tid; i < n; i += step) h[write_pos + i] = s[i];
+    }
+}
+
+// Deterministic synthetic signals: kind 0 = linear sine sweep 20 Hz -> 0.475 fs, 1 = white noise
+// uniform(-0.5,0.5) from splitmix64(seed, stream, n), 2 = 0.1*noise + sweep.
+JADE_DEVICE float synth_noise(unsigned long long seed, unsigned long long stream, unsigned long long n)
+{
+    unsigned long long z = seed + 0x9E3779B97F4A7C15ULL * (n + 1) + 0xD1B54A32D192ED03ULL * (stream + 1);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    z = z ^ (z >> 31);
+    return (float)(z >> 40) * (1.0f / 16777216.0f) - 0.5f;
+}
+JADE_KERNEL(256) synth_kernel(float* out, long long stream_stride, long long channel_stride, int nstreams, int channels,
+                              long long nsamples, int kind, unsigned long long seed, float fs)
+{
+    const long long total = (long long)nstreams * channels * nsamples;
+    const double dur = (double)nsamples / fs, f0 = 20.0, f1 = 0.475 * fs;
+    const double kr = (f1 - f0) / dur;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long n = i % nsamples;
+        const int ch = (int)((i / nsamples) % channels);
+        const int st = (int)(i / (nsamples * channels));
+        float v = 0.f;
+        if (kind != 1) {
+            const double tt = (double)n / fs;
+            double ph = f0 * tt + 0.5 * kr * tt * tt + 0.25 * ch; // cycles
+            ph -= floor(ph);
+            v = 0.5f * sinpif((float)(2.0 * ph));
+        }
+        if (kind == 1) v = synth_noise(seed, (unsigned long long)st * channels + ch, (unsigned long long)n);
+        if (kind == 2) v += 0.1f * synth_noise(seed, (unsigned long long)st * channels + ch, (unsigned long long)n);
+        out[st * stream_stride + ch * channel_stride + n] = v;
+    }
+}
+
+} // namespace jade

@@ -1,0 +1,73 @@
+// cuda_emu.h -- minimal CPU SIMT emulator used ONLY by the tests to execute the kernel source on the host.
+//
+// TEST INFRASTRUCTURE.  It exists because the build container has no GPU: the kernels in
+// jadespectrogram_b200/csrc/jade_kernels.cuh are compiled a second time with -DJADE_EMU by g++ and run with one OS
+// thread per CUDA thread (pthread barriers for __syncthreads/__syncwarp, a per-warp mailbox for shuffles), so that
+// index arithmetic, shared-memory layouts and synchronisation can be debugged before GPU time is spent.
+// Nothing in the product library includes this file and the product has no CPU code path.
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <pthread.h>
+#include <thread>
+#include <vector>
+
+struct float4 { float x, y, z, w; };
+struct float2 { float x, y; };
+struct dim3 { unsigned x = 1, y = 1, z = 1; dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
+
+namespace jade_emu {
+struct BlockState {
+    pthread_barrier_t block_bar;
+    std::vector<pthread_barrier_t> warp_bar;
+    std::vector<char> smem;
+};
+inline thread_local dim3 t_threadIdx, t_blockIdx;
+inline dim3 g_blockDim, g_gridDim;
+inline BlockState* g_block = nullptr;
+inline void* dyn_smem() { return g_block->smem.data(); }
+} // namespace jade_emu
+
+#define threadIdx jade_emu::t_threadIdx
+#define blockIdx jade_emu::t_blockIdx
+#define blockDim jade_emu::g_blockDim
+#define gridDim jade_emu::g_gridDim
+
+inline void __syncthreads() { pthread_barrier_wait(&jade_emu::g_block->block_bar); }
+inline void __syncwarp(unsigned = 0xffffffffu) { pthread_barrier_wait(&jade_emu::g_block->warp_bar[threadIdx.x >> 5]); }
+inline float sinpif(float x) { return (float)std::sin(M_PI * (double)x); }
+
+namespace jade_emu {
+// Launch kernel(args...) over grid x block threads; blocks run one after another.
+template <typename K, typename... A>
+void launch(K kernel, unsigned grid, unsigned block, size_t smem_bytes, A... args)
+{
+    g_blockDim = dim3(block);
+    g_gridDim = dim3(grid);
+    for (unsigned b = 0; b < grid; ++b) {
+        BlockState st;
+        st.smem.assign(smem_bytes + 64, 0);
+        pthread_barrier_init(&st.block_bar, nullptr, block);
+        const unsigned nw = (block + 31) / 32;
+        st.warp_bar.resize(nw);
+        for (unsigned w = 0; w < nw; ++w) {
+            unsigned cnt = (w + 1) * 32 <= block ? 32 : block - w * 32;
+            pthread_barrier_init(&st.warp_bar[w], nullptr, cnt);
+        }
+        g_block = &st;
+        std::vector<std::thread> th;
+        th.reserve(block);
+        for (unsigned t = 0; t < block; ++t)
+            th.emplace_back([=]() {
+                t_threadIdx = dim3(t);
+                t_blockIdx = dim3(b);
+                kernel(args...);
+            });
+        for (auto& x : th) x.join();
+        pthread_barrier_destroy(&st.block_bar);
+        for (auto& wb : st.warp_bar) pthread_barrier_destroy(&wb);
+        g_block = nullptr;
+    }
+}
+} // namespace jade_emu

@@ -1,0 +1,143 @@
+// emu_harness.cpp -- runs the product kernels (jade_kernels.cuh compiled with -DJADE_EMU) on the CPU SIMT emulator.
+// TEST INFRASTRUCTURE ONLY: used by tests/test_emu_kernels.py to debug kernel logic in the GPU-less build container.
+#define JADE_EMU 1
+#include "cuda_emu.h"
+
+#include "../../jadespectrogram_b200/csrc/jade_kernels.cuh"
+#include "../../jadespectrogram_b200/csrc/jade_host_tables.h"
+#include "../../include/jade_gpu.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+using jade::KParams;
+
+namespace {
+template <int T>
+void run_warp(const KParams& P, bool multi, bool pool, int grid)
+{
+    const int smem = jade::WarpCfg<T>::smem_bytes(P.npal, pool);
+    const int block = jade::WARP_KERNEL_WARPS * 32;
+    if (multi && pool) jade_emu::launch(jade::stft_warp_kernel<T, true, true>, grid, block, smem, P);
+    else if (multi) jade_emu::launch(jade::stft_warp_kernel<T, true, false>, grid, block, smem, P);
+    else if (pool) jade_emu::launch(jade::stft_warp_kernel<T, false, true>, grid, block, smem, P);
+    else jade_emu::launch(jade::stft_warp_kernel<T, false, false>, grid, block, smem, P);
+}
+template <int R1>
+void run_cta(const KParams& P, bool multi, bool pool, int grid)
+{
+    const int smem = jade::CtaCfg<R1>::smem_bytes(P.npal, pool);
+    const int block = 32 * R1;
+    if (multi && pool) jade_emu::launch(jade::stft_cta_kernel<R1, true, true>, grid, block, smem, P);
+    else if (multi) jade_emu::launch(jade::stft_cta_kernel<R1, true, false>, grid, block, smem, P);
+    else if (pool) jade_emu::launch(jade::stft_cta_kernel<R1, false, true>, grid, block, smem, P);
+    else jade_emu::launch(jade::stft_cta_kernel<R1, false, false>, grid, block, smem, P);
+}
+} // namespace
+
+extern "C" int emu_render(const jade_config* cin, const int32_t* palette, int npal, float min_db, float max_db,
+                          const float* samples, int nstreams, long long nsamples, long long first_col, int ncols,
+                          int grid, uint32_t* pix, float* db)
+{
+    jade_config c = *cin;
+    if (c.frames_per_block < 1) c.frames_per_block = 1;
+    if (c.block_stride <= 0) c.block_stride = c.hop * c.frames_per_block;
+    if (c.preroll < 0) c.preroll = c.fft_size;
+    if (c.power_scale <= 0.f) c.power_scale = 1.f;
+    const int N = c.fft_size, M = N / 2, B = M + 1;
+    std::vector<float> win;
+    jade_host::make_window(c.window, N, win);
+    const float g = (c.power_scale == 1.0f) ? 0.5f : 0.5f * std::sqrt(c.power_scale);
+    for (auto& v : win) v *= g;
+    std::vector<uint32_t> baked(npal);
+    for (int i = 0; i < npal; ++i) {
+        const uint32_t r = (palette[i] >> 16) & 255, gg = (palette[i] >> 8) & 255, b = palette[i] & 255;
+        baked[i] = c.pixel_format == JADE_PIX_RGBA8 ? (0xFF000000u | (b << 16) | (gg << 8) | r) : (0xFF000000u | (r << 16) | (gg << 8) | b);
+    }
+    jade_host::ValueRange range;
+    range.set(min_db, max_db, npal);
+    int k_lo = 0, k_hi = B, R = B;
+    bool pooled = false;
+    std::vector<jade::i2> rb;
+    if (c.row_map == JADE_ROWS_LINEAR_CROP) {
+        jade_host::linear_crop(c.sample_rate, B, c.fmin, c.fmax, k_lo, k_hi);
+        R = k_hi - k_lo;
+    } else if (c.row_map == JADE_ROWS_LOG_MAXPOOL) {
+        std::vector<int32_t> lo, hi;
+        jade_host::log_rows(c.sample_rate, N, c.rows, c.fmin, c.fmax, lo, hi);
+        rb.resize(c.rows);
+        for (int r = 0; r < c.rows; ++r) rb[r] = {lo[r], hi[r]};
+        R = c.rows;
+        pooled = true;
+    }
+    const bool multi = c.channels > 1 || c.mix_mode == JADE_MIX_MIN;
+    std::vector<jade_host::cpxf> twP, twI, twA, twH;
+    jade_host::twiddles(N, M + 1, 1, twP);
+    KParams P;
+    memset(&P, 0, sizeof P);
+    P.samples = samples;
+    P.stream_stride = (long long)c.channels * nsamples;
+    P.channel_stride = nsamples;
+    P.nsamples = nsamples;
+    P.sample_base = 0;
+    P.aligned2 = ((nsamples % 2) == 0 && (c.hop % 2) == 0 && (c.block_stride % 2) == 0 && (c.preroll % 2) == 0) ? 1 : 0;
+    P.N = N; P.M = M; P.B = B;
+    P.hop = c.hop; P.fb = c.frames_per_block; P.bstride = c.block_stride; P.preroll = c.preroll;
+    P.first_col = first_col; P.ncols = ncols; P.nstreams = nstreams;
+    P.channels = c.channels; P.mix_mode = c.mix_mode;
+    P.window = win.data();
+    P.twP = reinterpret_cast<const jade::cpx*>(twP.data());
+    P.palette = baked.data(); P.npal = npal;
+    P.pmin = range.mn; P.pmax = range.mx; P.pmaxc = range.maxclamp(); P.pmult = range.mult;
+    P.db_precise = c.db_precise;
+    P.pooled = pooled; P.R = R; P.k_lo = k_lo; P.k_hi = k_hi; P.flip = c.flip_y;
+    P.row_bins = rb.data();
+    P.pix = pix; P.db = db;
+    P.pix_stream_stride = (long long)ncols * R;
+    P.db_stream_stride = (long long)ncols * B;
+    std::vector<jade::cpx> se;
+    std::vector<float> sp;
+    if (N <= 2048) {
+        const int T = N / 64;
+        jade_host::twiddle_matrix(32 * T, 32, T, twI);
+        P.twI = reinterpret_cast<const jade::cpx*>(twI.data());
+        switch (T) {
+        case 1: run_warp<1>(P, multi, pooled, grid); break;
+        case 2: run_warp<2>(P, multi, pooled, grid); break;
+        case 4: run_warp<4>(P, multi, pooled, grid); break;
+        case 8: run_warp<8>(P, multi, pooled, grid); break;
+        case 16: run_warp<16>(P, multi, pooled, grid); break;
+        case 32: run_warp<32>(P, multi, pooled, grid); break;
+        default: return -1;
+        }
+    } else {
+        jade_host::twiddle_matrix(1024, 32, 32, twI);
+        P.twI = reinterpret_cast<const jade::cpx*>(twI.data());
+        const int Mfft = (N == 65536) ? N / 4 : M;
+        const int R1 = Mfft / 1024;
+        jade_host::twiddle_matrix(Mfft, R1, 1024, twA);
+        P.twA = reinterpret_cast<const jade::cpx*>(twA.data());
+        if (N == 65536) {
+            jade_host::twiddles(N / 2, N / 4 + 1, 1, twH);
+            P.twH = reinterpret_cast<const jade::cpx*>(twH.data());
+            se.resize((size_t)grid * (N / 4 + 1));
+            sp.resize((size_t)grid * (N / 2 + 1));
+            P.scratch_e = se.data();
+            P.scratch_p = sp.data();
+            const int smem = jade::CtaCfg<16>::smem_bytes(npal, false);
+            if (multi) jade_emu::launch(jade::stft_cta2_kernel<16, true>, grid, 512, smem, P);
+            else jade_emu::launch(jade::stft_cta2_kernel<16, false>, grid, 512, smem, P);
+        } else {
+            switch (R1) {
+            case 2: run_cta<2>(P, multi, pooled, grid); break;
+            case 4: run_cta<4>(P, multi, pooled, grid); break;
+            case 8: run_cta<8>(P, multi, pooled, grid); break;
+            case 16: run_cta<16>(P, multi, pooled, grid); break;
+            default: return -1;
+            }
+        }
+    }
+    return R;
+}

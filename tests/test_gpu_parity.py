@@ -1,0 +1,119 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (libjade_gpu.so), against the CPU oracle."""
+import numpy as np
+import pytest
+
+import parity
+import signals
+
+pytestmark = pytest.mark.gpu
+
+FS = 48000.0
+
+
+def _oracle_cols(oracle, x, **kw):
+    return oracle.render_batch(x, **kw)
+
+
+CASES = [
+    # N, hop, channels, window, mix
+    (1024, 512, 1, "hann", "absmean"),        # BASELINE config 1
+    (2048, 512, 2, "hann", "absmean"),        # config 2 geometry
+    (2048, 256, 1, "hann", "absmean"),        # config 4 geometry
+    (16384, 4096, 1, "blackmanharris", "absmean"),  # config 3 geometry
+    (64, 16, 1, "rect", "absmean"),
+    (128, 32, 2, "hamming", "max"),
+    (256, 64, 3, "flattop", "min"),
+    (512, 128, 2, "hannpoisson", "left"),
+    (512, 100, 2, "hann", "right"),           # odd-ish hop, still even
+    (1024, 205, 1, "hann", "absmean"),        # odd hop -> unaligned loads
+    (4096, 1024, 2, "hann", "absmean"),
+    (8192, 2048, 1, "hann", "max"),
+    (32768, 8192, 1, "hann", "absmean"),
+    (2048, 512, 1, "hann", "min"),            # Min with one channel clamps at 1e6
+]
+
+
+@pytest.mark.parametrize("N,hop,ch,window,mix", CASES)
+def test_batch_matches_oracle(gpu_engine_factory, oracle, N, hop, ch, window, mix):
+    ncols = 24 if N <= 4096 else 6
+    n = hop * ncols
+    x = signals.streams(2, ch, n, FS, kind="mix")
+    x[1] *= 40.0  # second stream is loud (drives the upper palette clamp and Min's 1e6 start)
+    eng = gpu_engine_factory(sample_rate=FS, fft_size=N, hop=hop, channels=ch, window=window, mix_mode=mix)
+    assert eng.columns_for(n) == ncols + 1
+    pix, db = eng.render_batch(x, want_db=True)
+    assert eng.kernel_launches > 0
+    B = N // 2 + 1
+    for s in range(2):
+        odb, opix = oracle.render_batch(x[s], fs=FS, fft_size=N, hop=hop, window=window, mix=mix, ncols=ncols + 1)
+        parity.check_db(db[s], odb, N, f"stream {s}")
+        parity.check_pixels(pix[s], opix, odb[:, ::-1], -50.0, 50.0, 256, f"stream {s}")
+    assert pix.shape == (2, ncols + 1, B)
+    assert (pix >> 24 == 0xFF).all()
+
+
+def test_n65536_matches_oracle(gpu_engine_factory, oracle):
+    N, hop, ncols = 65536, 1024, 5
+    n = N + hop * ncols
+    x = signals.streams(1, 1, n, 192000.0, kind="mix")
+    eng = gpu_engine_factory(sample_rate=192000.0, fft_size=N, hop=hop, channels=1, window="hann")
+    pix, db = eng.render_batch(x, first_col=60, ncols=ncols, want_db=True)
+    odb, opix = oracle.render_batch(x[0], fs=192000.0, fft_size=N, hop=hop, first_col=60, ncols=ncols)
+    parity.check_db(db[0], odb, N)
+    parity.check_pixels(pix[0], opix, odb[:, ::-1], -50.0, 50.0, 256)
+
+
+def test_silence_and_ring_init(gpu_engine_factory):
+    eng = gpu_engine_factory(sample_rate=FS, fft_size=1024, hop=512, channels=1, ring_columns=8)
+    x = np.zeros((1, 1, 4096), np.float32)
+    pix, db = eng.render_batch(x, want_db=True)
+    assert np.allclose(db, -110.0, atol=2e-4)  # 10*log10(1e-11)
+    ring = eng.read_ring_db()
+    assert (ring == -120.0).all()  # Spectrogram.cpp:223
+
+
+def test_streaming_equals_batch(gpu_engine_factory):
+    N, hop, ch = 2048, 512, 2
+    n = 512 * 40
+    x = signals.streams(1, ch, n, FS, kind="mix")
+    eng = gpu_engine_factory(sample_rate=FS, fft_size=N, hop=hop, channels=ch, ring_columns=64, max_push=512)
+    bpix, bdb = eng.render_batch(x, want_db=True)
+    eng.reset()
+    cols_p, cols_d = [], []
+    for b in range(40):
+        eng.push(x[0][:, b * 512:(b + 1) * 512])
+        p, d, first = eng.fetch()
+        assert first == len(cols_p) if len(p) else True
+        cols_p.extend(p)
+        cols_d.extend(d)
+    sp, sd = np.array(cols_p), np.array(cols_d)
+    assert sp.shape[0] == eng.columns_for(n)
+    assert np.array_equal(sd, bdb[0])
+    assert np.array_equal(sp, bpix[0])
+
+
+def test_block_emit_mode_matches_reference_counts(gpu_engine_factory, oracle):
+    """Reference emission pattern: feed 50 % -> 2 columns per N-sample block, newest column ends at (b+1)N - hop."""
+    N = 1024
+    eng = gpu_engine_factory(sample_rate=FS, fft_size=N, feed_percent=50, channels=1, memory_time_s=1.0)
+    sp = oracle.Spec()
+    sp.set_channels(1)
+    sp.set_samplerate(FS)
+    sp.set_memory_time_s(1.0)
+    sp.set_fftsize(N)
+    sp.set_feed_percent(oracle.FEED["p50"])
+    assert eng.W == sp.memory_size()
+    x = signals.streams(1, 1, N * 12, FS, kind="mix")[0]
+    mem = np.zeros((sp.memory_size(), sp.spectrum_size()), np.float32)
+    total = 0
+    for b in range(12):
+        blk = x[:, b * N:(b + 1) * N]
+        sp.process(blk)
+        eng.push(blk)
+        p, d, first = eng.fetch()
+        assert len(p) == 2 and first == total
+        newv, pos = sp.get_mem(mem)
+        if b > 0:
+            assert newv == 2
+        parity.check_db(d, mem[[(pos - 2) % eng.W, (pos - 1) % eng.W]], N, f"block {b}")
+        total += 2
