@@ -1,0 +1,343 @@
+#!/usr/bin/env python3
+"""bench.py -- STFT frames/s of the fused STFT->dB->palette path (BASELINE.json metric) on N GPUs of one node.
+
+Workload (config.workload = "cfg2-batch"): BASELINE configs[1] geometry -- stereo 48 kHz, FFT 2048, hop 512, Hann,
+AbsMean mix, dB, Jade/256 palette over -50..+50 dB, one ARGB32 pixel per bin (1025 rows) -- applied to a batch of
+independent synthetic streams (noise*0.1 + sine sweep).  A "step" is one pass of the hot path over that batch.
+
+  value   : frames/s with the inputs already resident in HBM (one kernel launch per step, CUDA events, max over ranks)
+  e2e     : frames/s through the reference-facing C ABI call jade_render_batch with pinned HOST buffers
+            (H2D of the samples and D2H of the pixel columns inside the timed region)
+  latency : per-block time of the real-time path (512-sample blocks, push + fetch through the C ABI)
+  roofline: algorithmic bytes (4*hop*C + 4*R per frame) / kernel time against the measured HBM copy bandwidth
+  cpu_baseline: the CPU oracle port timed on this box's host cores on a bounded sample
+
+`--impl reference` times the reference's CPU implementation of the same path (oracle port / compiled reference).
+"""
+import argparse
+import json
+import os
+import pathlib
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = pathlib.Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+FS = 48000.0
+N_FFT = 2048
+HOP = 512
+CHANNELS = 2
+ROWS = N_FFT // 2 + 1
+BYTES_ALG = 4 * HOP * CHANNELS + 4 * ROWS  # 8196 B per frame (SURVEY 8d / BASELINE.md section 3)
+STREAM_SECONDS = 20.0
+WORKLOAD = dict(workload="cfg2-batch", sample_rate=48000, fft_size=N_FFT, hop=HOP, channels=CHANNELS, window="hann",
+                mix="absmean", palette="jade256", range_db=[-50, 50], rows=ROWS, pixel="ARGB32")
+
+
+def measured_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        top = sorted(sm)[len(sm) // 2:]  # samples under load = upper half
+        return {"sm_mhz": statistics.median(top), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline(sample_seconds=12.0, threads=None):
+    """The oracle port (restated Spectrogram loop + FFT stand-in + restated palette) on the host cores."""
+    import ctypes as C
+
+    import numpy as np
+    import oracle_lib as O
+    import signals
+    threads = threads or os.cpu_count() or 1
+    cfg = O.BatchCfg(FS, N_FFT, HOP, O.WIN["hann"], CHANNELS, O.MIX["absmean"], O.PAL["jade"], 256, 0, -50.0, 50.0, 0)
+    x = signals.streams(1, CHANNELS, int(FS * 2.0), FS, kind="mix")[0]
+    frames = C.c_long(0)
+    # calibrate on one thread, then size the sample for ~sample_seconds of wall time on all threads
+    t0 = time.time()
+    fps1 = O.lib().jo_bench_batch(C.byref(cfg), x.reshape(-1), x.shape[1], 1, 1, C.byref(frames))
+    cal = time.time() - t0
+    per_stream = frames.value
+    nstreams = max(threads, int(sample_seconds * fps1 * threads / per_stream))
+    nstreams = (nstreams + threads - 1) // threads * threads
+    fps = O.lib().jo_bench_batch(C.byref(cfg), x.reshape(-1), x.shape[1], nstreams, threads, C.byref(frames))
+    return dict(value=fps, unit="frames/s", cores=threads, kind="port",
+                sample=f"{nstreams} streams x 2.0 s of the cfg2-batch workload ({frames.value} frames), "
+                       f"oracle port (restated Spectrogram.cpp loop, radix-2 FFT stand-in, restated palette); "
+                       f"1-thread rate {fps1:.0f} frames/s (calibration {cal:.1f} s)",
+                single_thread_value=fps1)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warm = args.steps, args.warmup
+    import ctypes as C
+
+    import oracle_lib as O
+    import signals
+    threads = os.cpu_count() or 1
+    cfg = O.BatchCfg(FS, N_FFT, HOP, O.WIN["hann"], CHANNELS, O.MIX["absmean"], O.PAL["jade"], 256, 0, -50.0, 50.0, 0)
+    x = signals.streams(1, CHANNELS, int(FS * 2.0), FS, kind="mix")[0]
+    frames = C.c_long(0)
+    lib = O.lib()
+    # one step = `threads` streams x 2 s (bounded sample of the workload); ~0.2-0.5 s per step
+    per_step_streams = threads
+    for _ in range(warm):
+        lib.jo_bench_batch(C.byref(cfg), x.reshape(-1), x.shape[1], per_step_streams, threads, C.byref(frames))
+    t0 = time.time()
+    total = 0
+    for _ in range(steps):
+        lib.jo_bench_batch(C.byref(cfg), x.reshape(-1), x.shape[1], per_step_streams, threads, C.byref(frames))
+        total += frames.value
+    dt = time.time() - t0
+    fps = total / dt
+    sample = (f"each step = {per_step_streams} streams x 2.0 s of cfg2-batch ({frames.value} frames) on {threads} host "
+              f"threads; CPU oracle port of Spectrogram.cpp:37-135 + CColorpalette lookup (FFT stand-in, parity unpinned)")
+    line = dict(impl="reference", metric="stft_frames_per_sec", value=fps, unit="frames/s", n_gpus=args.gpus, steps=steps,
+                warmup=warm, ms_per_step=dt / steps * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f32", data="synthetic", config=dict(WORKLOAD, streams_per_step=per_step_streams, seconds_per_stream=2.0),
+                cpu_baseline=dict(value=fps, unit="frames/s", cores=threads, kind="port", sample=sample),
+                e2e=dict(value=fps, unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import signals
+    from jadespectrogram_b200 import Engine, host_alloc, host_free
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    steps, warm = args.steps, max(args.warmup, 3)
+    S = args.streams
+    nsamp = int(FS * STREAM_SECONDS)
+    eng = Engine(local, sample_rate=FS, fft_size=N_FFT, hop=HOP, channels=CHANNELS, window="hann", mix_mode="absmean",
+                 max_push=512)
+    eng.set_palette_scheme("jade", 256)
+    eng.set_value_range(-50.0, 50.0)
+    ncols = eng.columns_for(nsamp)
+    frames_step = S * ncols
+
+    # ---- inputs resident in HBM (generated on the device), outputs in HBM
+    d_in = torch.empty((S, CHANNELS, nsamp), dtype=torch.float32, device=dev)
+    d_pix = torch.empty((S, ncols, ROWS), dtype=torch.int32, device=dev)
+    # a dedicated (non-default) stream: kernels, timing events and the engine all use this one stream
+    tstream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
+    eng.synth_device(d_in.data_ptr(), S, CHANNELS, nsamp, CHANNELS * nsamp, nsamp, kind="mix", seed=20240601 + rank,
+                     cuda_stream=stream)
+    torch.cuda.synchronize()
+
+    def step():
+        eng.render_device(d_in.data_ptr(), S, nsamp, CHANNELS * nsamp, nsamp, 0, ncols, d_pix.data_ptr(), None, stream)
+
+    for _ in range(warm):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = eng.kernel_launches
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    torch.cuda.synchronize()
+    ev[0].record()
+    for i in range(steps):
+        step()
+        ev[i + 1].record()
+    torch.cuda.synchronize()
+    launches = eng.kernel_launches - l0
+    total_ms = ev[0].elapsed_time(ev[steps])
+    per_launch_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(steps)]
+    # keep the GPU busy a little longer so the clock sampler sees the load (untimed)
+    t_end = time.time() + 0.6
+    while rank == 0 and time.time() < t_end:
+        step()
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    max_ms = float(t.item())
+    value = frames_step * steps * world / (max_ms * 1e-3)
+    kernel_ms = statistics.mean(per_launch_ms)
+
+    if args.only_kernel:  # short command for ncu captures: no e2e / latency / CPU legs
+        if rank == 0:
+            print(json.dumps(dict(metric="stft_frames_per_sec", value=value, unit="frames/s", n_gpus=world, steps=steps,
+                                  kernel_ms=kernel_ms, gpu_launches=int(launches), note="--only-kernel")))
+        eng.close()
+        return
+
+    # ---- e2e: host buffers through jade_render_batch (H2D + kernel + D2H inside the timed region)
+    Se = min(S, args.e2e_streams)
+    h_in = host_alloc((Se, CHANNELS, nsamp), np.float32)
+    h_pix = host_alloc((Se, ncols, ROWS), np.uint32)
+    h_in[:] = d_in[:Se].cpu().numpy()
+    e2e_steps = max(2, min(steps, 6))
+    for _ in range(2):
+        eng.render_batch(h_in, out_pix=h_pix)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        eng.render_batch(h_in, out_pix=h_pix)
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = Se * ncols * e2e_steps * world / float(te.item())
+    check = int(h_pix[0, ncols // 2].astype(np.uint64).sum())  # the step's result is read on the host
+    e2e = dict(value=e2e_value, unit="frames/s", h2d_bytes_per_step=int(h_in.nbytes), d2h_bytes_per_step=int(h_pix.nbytes),
+               steps=e2e_steps, streams_per_step=Se, api="jade_render_batch (pinned host buffers)", checksum=check)
+    host_free(h_in)
+    host_free(h_pix)
+
+    # ---- real-time path latency: 512-sample stereo blocks, push + fetch through the C ABI
+    lat = None
+    if rank == 0:
+        eng.reset()
+        blk = signals.streams(1, CHANNELS, 512 * 64, FS, kind="mix")[0]
+        ts = []
+        nblk = args.latency_blocks
+        for b in range(nblk + 200):
+            piece = blk[:, (b % 64) * 512:(b % 64 + 1) * 512]
+            t0 = time.perf_counter()
+            eng.push(piece)
+            p, _, _ = eng.fetch(max_cols=4, want_db=False)
+            t1 = time.perf_counter()
+            if b >= 200:
+                ts.append((t1 - t0) * 1e6)
+        ts.sort()
+        lat = dict(p50_us=ts[len(ts) // 2], p99_us=ts[int(len(ts) * 0.99)], blocks=nblk, block_samples=512,
+                   path="jade_push_samples + jade_fetch_columns (1 column per block), host timer around both calls")
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        achieved = BYTES_ALG * frames_step / (kernel_ms * 1e-3) / 1e9
+        traffic = None
+        tp = ROOT / "profiles" / "traffic.json"
+        if tp.exists():
+            try:
+                traffic = json.loads(tp.read_text()).get("cfg2-batch")
+            except Exception:
+                traffic = None
+        cpu = cpu_baseline(args.cpu_seconds) if not args.no_cpu else None
+        line = dict(
+            metric="stft_frames_per_sec", value=value, unit="frames/s", n_gpus=world, steps=steps, warmup=warm,
+            ms_per_step=max_ms / steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+            data="synthetic (0.1*white noise + linear sine sweep per stream, generated on the device)",
+            config=dict(WORKLOAD, streams_per_gpu=S, seconds_per_stream=STREAM_SECONDS, frames_per_step_per_gpu=frames_step,
+                        input_bytes_per_step_per_gpu=int(d_in.numel() * 4), output_bytes_per_step_per_gpu=int(d_pix.numel() * 4),
+                        l2_policy="inputs+outputs per step exceed L2 (126 MB) many times; no explicit flush",
+                        parallelism=f"streams sharded over {world} GPU(s), no collective", kernel=eng.kernel_name),
+            e2e=e2e, gpu_launches=int(launches), clocks=clocks, latency=lat,
+            roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic,
+                          peak_source=peak_src, bytes_per_frame=BYTES_ALG, frames_per_launch=frames_step,
+                          kernel_ms=kernel_ms),
+            cpu_baseline=cpu)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    eng.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--streams", type=int, default=256, help="streams per GPU per step")
+    ap.add_argument("--e2e-streams", type=int, default=64)
+    ap.add_argument("--latency-blocks", type=int, default=2000)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--only-kernel", action="store_true", help="device-resident loop only (for ncu)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

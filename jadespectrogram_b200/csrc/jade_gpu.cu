@@ -38,17 +38,22 @@ struct KernelChoice {
     int family = 0; // 0 warp, 1 cta, 2 cta2
 };
 
+// (mix kind, general epilogue) -> kernel instantiation; Max/Min only exist with the general epilogue
 template <int T>
-kernel_fn pick_warp(bool multi, bool pool)
+kernel_fn pick_warp(int mixk, bool general)
 {
-    if (multi) return pool ? (kernel_fn)jade::stft_warp_kernel<T, true, true> : (kernel_fn)jade::stft_warp_kernel<T, true, false>;
-    return pool ? (kernel_fn)jade::stft_warp_kernel<T, false, true> : (kernel_fn)jade::stft_warp_kernel<T, false, false>;
+    if (mixk == jade::MIX_SEL) return (kernel_fn)jade::stft_warp_kernel<T, jade::MIX_SEL, true>;
+    if (mixk == jade::MIX_SUM)
+        return general ? (kernel_fn)jade::stft_warp_kernel<T, jade::MIX_SUM, true> : (kernel_fn)jade::stft_warp_kernel<T, jade::MIX_SUM, false>;
+    return general ? (kernel_fn)jade::stft_warp_kernel<T, jade::MIX_NONE, true> : (kernel_fn)jade::stft_warp_kernel<T, jade::MIX_NONE, false>;
 }
 template <int R1>
-kernel_fn pick_cta(bool multi, bool pool)
+kernel_fn pick_cta(int mixk, bool general)
 {
-    if (multi) return pool ? (kernel_fn)jade::stft_cta_kernel<R1, true, true> : (kernel_fn)jade::stft_cta_kernel<R1, true, false>;
-    return pool ? (kernel_fn)jade::stft_cta_kernel<R1, false, true> : (kernel_fn)jade::stft_cta_kernel<R1, false, false>;
+    if (mixk == jade::MIX_SEL) return (kernel_fn)jade::stft_cta_kernel<R1, jade::MIX_SEL, true>;
+    if (mixk == jade::MIX_SUM)
+        return general ? (kernel_fn)jade::stft_cta_kernel<R1, jade::MIX_SUM, true> : (kernel_fn)jade::stft_cta_kernel<R1, jade::MIX_SUM, false>;
+    return general ? (kernel_fn)jade::stft_cta_kernel<R1, jade::MIX_NONE, true> : (kernel_fn)jade::stft_cta_kernel<R1, jade::MIX_NONE, false>;
 }
 
 struct DevBuf {
@@ -113,7 +118,9 @@ struct jade_engine {
     int N = 0, M = 0, B = 0, R = 0, W = 0;
     int k_lo = 0, k_hi = 0;
     KernelChoice kc;
-    bool multi = false, pooled = false;
+    int mixk = 0;          // jade::MIX_NONE / MIX_SUM / MIX_SEL
+    bool general = false;  // general (rolled) epilogue: pooled / cropped rows, precise dB, non-2^n channel mean, Max/Min
+    bool pooled = false;
 
     // tables
     std::vector<float> h_window;       // unit-RMS reference window
@@ -176,7 +183,8 @@ int choose_kernel(jade_engine* e)
 {
     KernelChoice kc;
     const int N = e->N;
-    const bool mu = e->multi, po = e->pooled;
+    const int mu = e->mixk;
+    const bool po = e->general;
     if (N <= 2048) {
         const int T = N / 64;
         kc.family = 0;
@@ -208,7 +216,9 @@ int choose_kernel(jade_engine* e)
         kc.family = 2;
         kc.threads = 32 * 16;
         snprintf(kc.name, sizeof kc.name, "cta2<16>");
-        kc.fn = mu ? (kernel_fn)jade::stft_cta2_kernel<16, true> : (kernel_fn)jade::stft_cta2_kernel<16, false>;
+        kc.fn = mu == jade::MIX_SEL ? (kernel_fn)jade::stft_cta2_kernel<16, jade::MIX_SEL>
+              : mu == jade::MIX_SUM ? (kernel_fn)jade::stft_cta2_kernel<16, jade::MIX_SUM>
+                                    : (kernel_fn)jade::stft_cta2_kernel<16, jade::MIX_NONE>;
         kc.smem = jade::CtaCfg<16>::smem_bytes(e->npal, false);
     } else {
         return fail(e, JADE_ERR_ARG, "unsupported fft_size %d (power of two in [64,65536])", N);
@@ -533,7 +543,15 @@ int jade_configure(jade_engine* e, const jade_config* cin)
         return fail(e, JADE_ERR_ARG, "bad row_map %d", c.row_map);
     }
     e->cfg.rows = e->R;
-    e->multi = c.channels > 1 || c.mix_mode == JADE_MIX_MIN;
+    {
+        const int contributing = (c.mix_mode == JADE_MIX_LEFT || c.mix_mode == JADE_MIX_RIGHT) ? 1 : c.channels;
+        if (c.mix_mode == JADE_MIX_MIN || (c.mix_mode == JADE_MIX_MAX && contributing > 1)) e->mixk = jade::MIX_SEL;
+        else if (c.mix_mode == JADE_MIX_ABSMEAN && contributing > 1) e->mixk = jade::MIX_SUM;
+        else e->mixk = jade::MIX_NONE;
+        const bool pow2ch = (c.channels & (c.channels - 1)) == 0;
+        e->general = e->pooled || c.row_map != JADE_ROWS_IDENTITY || c.db_precise != 0 || e->mixk == jade::MIX_SEL ||
+                     (e->mixk == jade::MIX_SUM && !pow2ch);
+    }
 
     // tables
     if (int r = upload_window(e)) return r;

@@ -92,12 +92,20 @@ struct KParams {
     const cpx* twH;         // [M/2+1]  W_{N/2}^k  (split of the half-size real FFTs)
 };
 
-JADE_DEVICE float to_db(float p, int precise)
+// 10*log10(p + 1e-11) (Spectrogram.cpp:36,107).  Fast: one MUFU.LG2 + one FMUL (|err| ~ 1e-5 dB).
+JADE_DEVICE float to_db_fast(float p) { return 3.01029995663981195f * JADE_LOG2F(p + 1e-11f); }
+// Exactly the reference's arithmetic: float add, double log10, double multiply, float store.
+#if defined(__CUDACC__)
+__device__ __noinline__
+#else
+inline
+#endif
+float to_db_precise(float p)
 {
-    const float sh = p + 1e-11f; // Spectrogram.cpp:36,107
-    if (precise) return (float)(10.0 * log10((double)sh));
-    return 3.01029995663981195f * JADE_LOG2F(sh);
+    const float sh = p + 1e-11f;
+    return (float)(10.0 * log10((double)sh));
 }
+JADE_DEVICE float to_db(float p, int precise) { return precise ? to_db_precise(p) : to_db_fast(p); }
 
 // CColorPalette::getRGBColor (CColorpalette.h:32-47) on the baked table.  The index is additionally clamped at 0
 // (the reference would read out of bounds when m_Min > m_Max).
@@ -112,12 +120,8 @@ JADE_DEVICE uint32_t colour_of(float v, const KParams& P, const uint32_t* pal)
     return pal[idx];
 }
 
-JADE_DEVICE cpx load_pair(const float* JADE_RESTRICT x, long long idx, long long ns, bool fast)
+JADE_DEVICE cpx load_pair_guarded(const float* JADE_RESTRICT x, long long idx, long long ns)
 {
-    if (fast) {
-        const cpx* p = reinterpret_cast<const cpx*>(x + idx);
-        return *p;
-    }
     cpx r;
     r.x = (idx >= 0 && idx < ns) ? x[idx] : 0.f;
     r.y = (idx + 1 >= 0 && idx + 1 < ns) ? x[idx + 1] : 0.f;
@@ -140,18 +144,23 @@ JADE_DEVICE cpx split_value(cpx zk, cpx zp, cpx w)
     return mk(ax + fm(w.x, by, w.y * bx), ay - fm(w.x, bx, -(w.y * by)));
 }
 
-JADE_DEVICE void mix_init(float& a, int mode) { a = (mode == K_MIX_MIN) ? 1000000.0f : 0.0f; }
-JADE_DEVICE void mix_add(float& a, float p, int mode, int ch, int right_ch)
+// Channel mix (Spectrogram.cpp:64-106) as a compile-time kind so the per-bin code stays branch-free:
+//   MIX_NONE : one contributing channel (mono, Left, Right)          acc = p
+//   MIX_SUM  : AbsMean                                               acc += p, finally / channels
+//   MIX_SEL  : Max (start 0) / Min (start 1e6)                       acc = max/min(acc, p)
+enum { MIX_NONE = 0, MIX_SUM = 1, MIX_SEL = 2 };
+template <int MIXK>
+JADE_DEVICE float mix_init(int mode)
 {
-    switch (mode) {
-    case K_MIX_ABSMEAN: a += p; break;
-    case K_MIX_MAX: if (p > a) a = p; break;
-    case K_MIX_MIN: if (p < a) a = p; break;
-    case K_MIX_LEFT: if (ch == 0) a = p; break;
-    default: if (ch == right_ch) a = p; break;
-    }
+    return (MIXK == MIX_SEL && mode == K_MIX_MIN) ? 1000000.0f : 0.0f;
 }
-JADE_DEVICE float mix_done(float a, int mode, float nch) { return mode == K_MIX_ABSMEAN ? JADE_FDIV(a, nch) : a; }
+template <int MIXK>
+JADE_DEVICE void mix_add(float& a, float p, int mode)
+{
+    if (MIXK == MIX_NONE) a = p;
+    else if (MIXK == MIX_SUM) a += p;
+    else a = (mode == K_MIX_MIN) ? ((p < a) ? p : a) : ((p > a) ? p : a);
+}
 
 struct ColOut {
     uint32_t* pix; // column base or null
@@ -167,29 +176,48 @@ JADE_DEVICE ColOut col_out(const KParams& P, int stream, long long j)
 }
 JADE_DEVICE long long frame_start(const KParams& P, long long j)
 {
+    if (P.fb == 1) return j * (long long)P.bstride - P.preroll - P.sample_base;
     return (j / P.fb) * (long long)P.bstride + (j % P.fb) * (long long)P.hop - P.preroll - P.sample_base;
 }
-
-// dB + pixel for one bin of the un-pooled row map
-JADE_DEVICE void emit_bin(const KParams& P, const uint32_t* pal, const ColOut& o, int k, float power)
+// channels that contribute to the mix (Left / Right need a single one)
+JADE_DEVICE void channel_range(const KParams& P, int& ch0, int& ch1)
 {
-    const float d = to_db(power, P.db_precise);
-    if (o.db) o.db[k] = d;
-    if (o.pix && k >= P.k_lo && k < P.k_hi) {
-        const int row = P.flip ? (P.k_hi - 1 - k) : (k - P.k_lo);
-        o.pix[row] = colour_of(d, P, pal);
+    ch0 = 0;
+    ch1 = P.channels;
+    if (P.mix_mode == K_MIX_LEFT) ch1 = 1;
+    if (P.mix_mode == K_MIX_RIGHT) {
+        ch0 = P.channels > 1 ? 1 : 0;
+        ch1 = ch0 + 1;
     }
 }
-// pooled rows from a power spectrum (shared or global memory); threads tid..step
-JADE_DEVICE void emit_pooled(const KParams& P, const uint32_t* pal, const ColOut& o, const float* spec, int tid, int step)
+
+// General ("slow") epilogue from a mixed power spectrum in shared or global memory: any row map, precise dB,
+// non power-of-two channel means.  Rolled loops: small code, only used off the headline path.
+// Phase 1 (per bin) must be followed by a barrier of the participating threads before phase 2 (pooled rows).
+JADE_DEVICE void emit_general_bins(const KParams& P, const uint32_t* pal, const ColOut& o, float* spec, int tid, int step)
 {
-    if (!o.pix) return;
+    const bool mean = P.mix_mode == K_MIX_ABSMEAN && P.channels > 1;
+    const float nchf = (float)P.channels;
+    for (int k = tid; k < P.B; k += step) {
+        float p = spec[k];
+        if (mean) p = JADE_FDIV(p, nchf);
+        spec[k] = p;
+        if (o.db || !P.pooled) {
+            const float d = to_db(p, P.db_precise);
+            if (o.db) o.db[k] = d;
+            if (!P.pooled && o.pix && k >= P.k_lo && k < P.k_hi)
+                o.pix[P.flip ? (P.k_hi - 1 - k) : (k - P.k_lo)] = colour_of(d, P, pal);
+        }
+    }
+}
+JADE_DEVICE void emit_general_rows(const KParams& P, const uint32_t* pal, const ColOut& o, const float* spec, int tid, int step)
+{
+    if (!P.pooled || !o.pix) return;
     for (int r = tid; r < P.R; r += step) {
         const i2 rb = P.row_bins[r];
         float mx = spec[rb.lo];
         for (int k = rb.lo + 1; k < rb.hi; ++k) mx = fmaxf(mx, spec[k]);
-        const float d = to_db(mx, P.db_precise);
-        o.pix[P.flip ? (P.R - 1 - r) : r] = colour_of(d, P, pal);
+        o.pix[P.flip ? (P.R - 1 - r) : r] = colour_of(to_db(mx, P.db_precise), P, pal);
     }
 }
 
@@ -197,25 +225,41 @@ JADE_DEVICE void emit_pooled(const KParams& P, const uint32_t* pal, const ColOut
 // Warp-level M = 32*T point complex FFT, T lanes per transform (F = 32/T transforms per warp).
 // in : v[brev5(n1)] = z[s + T*n1]           (s = lane % T)
 // out: u[i*T + k2]  = Z[(s + T*i) + 32*k2]  (i < 32/T, k2 < T)  i.e. bin k = s + T*q sits in u[(q % F)*T + q / F]
-// xw : this transform's shared-memory scratch (M complex words); synchronised with __syncwarp only.
+// xw : this transform's shared-memory scratch; synchronised with __syncwarp only.
+// PADDED = true : transpose through rows of T+1 words (needs 32*(T+1) words).  Every access is base+immediate and
+//                 conflict-free for 8-byte words.
+// PADDED = false: in-place XOR swizzle inside exactly 32*T words (used on the CTA kernels' row buffers).
 // ---------------------------------------------------------------------------------------------------------
-template <int T>
+template <int T, bool PADDED>
 JADE_DEVICE void warp_fft(cpx* v, cpx* u, cpx* xw, const cpx* twI, int s)
 {
     constexpr int F = 32 / T;
     fft_dit<32>(v);
+    const cpx* tw = twI + s;
+    if (PADDED) {
+        cpx* wr = xw + s;
 #pragma unroll
-    for (int k1 = 0; k1 < 32; ++k1) {
-        const cpx t = (k1 == 0) ? v[0] : cmul(v[k1], twI[k1 * T + s]);
-        xw[k1 * T + (s ^ (k1 & (T - 1)))] = t;
-    }
-    __syncwarp();
+        for (int k1 = 0; k1 < 32; ++k1) wr[k1 * (T + 1)] = (k1 == 0) ? v[0] : cmul(v[k1], tw[k1 * T]);
+        __syncwarp();
+        const cpx* rd = xw + s * (T + 1);
 #pragma unroll
-    for (int i = 0; i < F; ++i) {
-        const int k1 = s + T * i;
+        for (int i = 0; i < F; ++i) {
 #pragma unroll
-        for (int jx = 0; jx < T; ++jx) u[i * T + brev(jx, ilog2c(T))] = xw[k1 * T + (jx ^ s)];
-        fft_dit<T>(u + i * T);
+            for (int jx = 0; jx < T; ++jx) u[i * T + brev(jx, ilog2c(T))] = rd[T * i * (T + 1) + jx];
+            fft_dit<T>(u + i * T);
+        }
+    } else {
+#pragma unroll
+        for (int k1 = 0; k1 < 32; ++k1)
+            xw[k1 * T + (s ^ (k1 & (T - 1)))] = (k1 == 0) ? v[0] : cmul(v[k1], tw[k1 * T]);
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < F; ++i) {
+            const int k1 = s + T * i;
+#pragma unroll
+            for (int jx = 0; jx < T; ++jx) u[i * T + brev(jx, ilog2c(T))] = xw[k1 * T + (jx ^ s)];
+            fft_dit<T>(u + i * T);
+        }
     }
     __syncwarp();
 }
@@ -231,7 +275,9 @@ struct WarpCfg {
     static constexpr int N = 2 * M;
     static constexpr int B = M + 1;
     static constexpr int F = 32 / T;
-    static constexpr int FS = M + (T < 16 ? T : 0);      // per-transform stride in the exchange buffer (complex words)
+    // per-transform scratch (complex words): 32 rows of T+1 (transpose) / M+1 natural-order words; for T < 16 the
+    // stride is made == T (mod 16) so that the transforms sharing a half-warp hit disjoint banks
+    static constexpr int FS = 32 * T + 32 + (T < 16 ? T : 0);
     static constexpr int SPEC_STRIDE = ((B + 3) / 4) * 4; // floats
     // shared memory layout in bytes
     static constexpr int off_twI = 0;
@@ -239,14 +285,16 @@ struct WarpCfg {
     static constexpr int off_twP = off_win + M * 8;
     static constexpr int off_pal = off_twP + ((M + 1) * 8 + 15) / 16 * 16;
     static JADE_HD int off_xch(int npal) { return off_pal + (npal * 4 + 15) / 16 * 16; }
-    static JADE_HD int smem_bytes(int npal, bool pooled)
+    static JADE_HD int smem_bytes(int npal, bool general)
     {
-        return off_xch(npal) + WARP_KERNEL_WARPS * F * FS * 8 + (pooled ? WARP_KERNEL_WARPS * F * SPEC_STRIDE * 4 : 0);
+        return off_xch(npal) + WARP_KERNEL_WARPS * F * FS * 8 + (general ? WARP_KERNEL_WARPS * F * SPEC_STRIDE * 4 : 0);
     }
 };
 
-template <int T, bool MULTI, bool POOL>
-JADE_KERNEL(WARP_KERNEL_WARPS * 32) stft_warp_kernel(const KParams P)
+// GENERAL = false: headline path (identity rows, hardware log2, exact reciprocal for the mean); all addressing is
+//                  base + immediate.  GENERAL = true: every other option through emit_general.
+template <int T, int MIXK, bool GENERAL>
+JADE_KERNEL(WARP_KERNEL_WARPS * 32, (T >= 4 && !GENERAL) ? 2 : 1) stft_warp_kernel(const KParams P)
 {
     using Cfg = WarpCfg<T>;
     constexpr int M = Cfg::M, N = Cfg::N, F = Cfg::F, FS = Cfg::FS;
@@ -269,87 +317,98 @@ JADE_KERNEL(WARP_KERNEL_WARPS * 32) stft_warp_kernel(const KParams P)
     const int f = lane / T, s = lane % T;
     cpx* xw = s_xch + (warp * F + f) * FS;
     float* spec = s_spec + (warp * F + f) * Cfg::SPEC_STRIDE;
+    const cpx* win_l = s_win + s;
+    const cpx* twP_l = s_twP + s;
+    cpx* nat_wr = xw + s;            // natural-order copy of Z: word k = s + T*q
+    const cpx* nat_rd = xw + (T - s); // partner Z[M-k] = word (T - s) + T*(31 - q); word M duplicates Z[0]
 
-    const long long groups = (P.ncols + F - 1) / F;
-    const long long total = groups * P.nstreams;
-    const int right_ch = P.channels > 1 ? 1 : 0;
-    const float nchf = (float)P.channels;
+    const unsigned groups = (unsigned)((P.ncols + F - 1) / F);
+    const unsigned total = groups * (unsigned)P.nstreams;
+    int ch0, ch1;
+    channel_range(P, ch0, ch1);
 
-    for (long long g = (long long)blockIdx.x * WARP_KERNEL_WARPS + warp; g < total;
-         g += (long long)gridDim.x * WARP_KERNEL_WARPS) {
+    for (unsigned g = blockIdx.x * WARP_KERNEL_WARPS + warp; g < total; g += gridDim.x * WARP_KERNEL_WARPS) {
         const int stream = (int)(g / groups);
-        long long jrel = (g % groups) * F + f;
+        const int jfirst = (int)(g - (unsigned)stream * groups) * F; // first column of this warp's group
+        int jrel = jfirst + f;
         const bool active = jrel < P.ncols;
         if (!active) jrel = P.ncols - 1;
         const long long j = P.first_col + jrel;
         const long long st = frame_start(P, j);
-        const bool fast = P.aligned2 && st >= 0 && st + N <= P.nsamples;
+        // warp-uniform: every transform of this warp lies inside the signal (frame starts are monotone in j)
+        bool fast;
+        if (F == 1) {
+            fast = P.aligned2 && st >= 0 && st + N <= P.nsamples;
+        } else {
+            const int jlast = (jfirst + F - 1 < P.ncols) ? jfirst + F - 1 : P.ncols - 1;
+            fast = P.aligned2 && frame_start(P, P.first_col + jfirst) >= 0 &&
+                   frame_start(P, P.first_col + jlast) + N <= P.nsamples;
+        }
 
         float acc[33];
-        if (MULTI) {
 #pragma unroll
-            for (int q = 0; q < 33; ++q) mix_init(acc[q], P.mix_mode);
-        }
-        // Left / Right need a single channel only
-        int ch0 = 0, ch1 = P.channels;
-        if (MULTI && P.mix_mode == K_MIX_LEFT) ch1 = 1;
-        if (MULTI && P.mix_mode == K_MIX_RIGHT) { ch0 = right_ch; ch1 = right_ch + 1; }
+        for (int q = 0; q < 33; ++q) acc[q] = mix_init<MIXK>(P.mix_mode);
 
         for (int ch = ch0; ch < ch1; ++ch) {
             const float* x = P.samples + stream * P.stream_stride + ch * P.channel_stride;
             cpx v[32], u[32];
+            if (fast) {
+                const cpx* xz = reinterpret_cast<const cpx*>(x + st) + s;
 #pragma unroll
-            for (int n1 = 0; n1 < 32; ++n1) {
-                const int m = s + T * n1;
-                const cpx z = load_pair(x, st + 2 * m, P.nsamples, fast);
-                const cpx w = s_win[m];
-                v[brev(n1, 5)] = mk(z.x * w.x, z.y * w.y);
+                for (int n1 = 0; n1 < 32; ++n1) {
+                    const cpx z = xz[T * n1];
+                    const cpx w = win_l[T * n1];
+                    v[brev(n1, 5)] = mk(z.x * w.x, z.y * w.y);
+                }
+            } else { // frame touches the signal boundary or is unaligned: guarded loads staged through shared memory
+                for (int m = s; m < M; m += T) {
+                    const cpx z = load_pair_guarded(x, st + 2 * m, P.nsamples);
+                    const cpx w = s_win[m];
+                    xw[m] = mk(z.x * w.x, z.y * w.y);
+                }
+#pragma unroll
+                for (int n1 = 0; n1 < 32; ++n1) v[brev(n1, 5)] = nat_wr[T * n1]; // the thread's own words
+                __syncwarp();
             }
-            warp_fft<T>(v, u, xw, s_twI, s);
-            // natural-order copy of Z for the partner reads of the split
+            warp_fft<T, true>(v, u, xw, s_twI, s);
 #pragma unroll
-            for (int i = 0; i < F; ++i)
-#pragma unroll
-                for (int k2 = 0; k2 < T; ++k2) xw[(s + T * i) + 32 * k2] = u[i * T + k2];
+            for (int q = 0; q < 32; ++q) nat_wr[T * q] = u[(q % F) * T + q / F];
+            if (s == 0) xw[M] = u[0];
             __syncwarp();
 #pragma unroll
             for (int q = 0; q < 32; ++q) {
-                const int k = s + T * q;
-                const cpx zk = u[(q % F) * T + q / F];
-                const cpx zp = xw[(M - k) & (M - 1)];
-                const float p = split_power(zk, zp, s_twP[k]);
-                if (MULTI) mix_add(acc[q], p, P.mix_mode, ch, right_ch);
-                else acc[q] = p;
+                const float p = split_power(u[(q % F) * T + q / F], nat_rd[T * (31 - q)], twP_l[T * q]);
+                mix_add<MIXK>(acc[q], p, P.mix_mode);
             }
-            {   // Nyquist bin k = M (kept by sub-lane 0; computed by all lanes to stay convergent)
+            {   // Nyquist bin k = M (kept by sub-lane 0; computed by every lane to stay convergent)
                 const cpx z0 = xw[0];
-                const float p = split_power(z0, z0, s_twP[M]);
-                if (MULTI) mix_add(acc[32], p, P.mix_mode, ch, right_ch);
-                else acc[32] = p;
+                mix_add<MIXK>(acc[32], split_power(z0, z0, s_twP[M]), P.mix_mode);
             }
             __syncwarp();
-        }
-        if (MULTI) {
-#pragma unroll
-            for (int q = 0; q < 33; ++q) acc[q] = mix_done(acc[q], P.mix_mode, nchf);
         }
         const ColOut o = active ? col_out(P, stream, j) : ColOut{nullptr, nullptr};
-        if (!POOL) {
+        if (!GENERAL) {
+            // identity rows: bin k = s + T*q -> row (flip ? M - k : k); mean over 2^n channels is an exact multiply
+            const float scale = (MIXK == MIX_SUM) ? (1.0f / (float)P.channels) : 1.0f;
+            uint32_t* prow = o.pix ? (P.flip ? o.pix + (M - s) : o.pix + s) : nullptr;
+            float* drow = o.db ? o.db + s : nullptr;
+            const int pstep = P.flip ? -T : T;
 #pragma unroll
-            for (int q = 0; q < 32; ++q) emit_bin(P, s_pal, o, s + T * q, acc[q]);
-            if (s == 0) emit_bin(P, s_pal, o, M, acc[32]);
+            for (int q = 0; q < 33; ++q) {
+                if (q == 32 && s != 0) break;
+                const float d = to_db_fast(MIXK == MIX_SUM ? acc[q] * scale : acc[q]);
+                const uint32_t c = colour_of(d, P, s_pal);
+                if (drow) drow[T * q] = d;
+                if (prow) prow[pstep * q] = c;
+            }
         } else {
 #pragma unroll
-            for (int q = 0; q < 32; ++q) {
-                spec[s + T * q] = acc[q];
-                if (o.db) o.db[s + T * q] = to_db(acc[q], P.db_precise);
-            }
-            if (s == 0) {
-                spec[M] = acc[32];
-                if (o.db) o.db[M] = to_db(acc[32], P.db_precise);
-            }
+            for (int q = 0; q < 32; ++q) spec[s + T * q] = acc[q];
+            if (s == 0) spec[M] = acc[32];
             __syncwarp();
-            emit_pooled(P, s_pal, o, spec, s, T);
+            emit_general_bins(P, s_pal, o, spec, s, T);
+            __syncwarp();
+            emit_general_rows(P, s_pal, o, spec, s, T);
             __syncwarp();
         }
     }
@@ -369,7 +428,7 @@ struct CtaCfg {
     static constexpr int off_twI = off_row + R1 * RS * 8;
     static constexpr int off_pal = off_twI + 1024 * 8;
     static JADE_HD int off_spec(int npal) { return off_pal + (npal * 4 + 15) / 16 * 16; }
-    static JADE_HD int smem_bytes(int npal, bool pooled) { return off_spec(npal) + (pooled ? ((B + 3) / 4) * 16 : 0); }
+    static JADE_HD int smem_bytes(int npal, bool general) { return off_spec(npal) + (general ? ((B + 3) / 4) * 16 : 0); }
 };
 
 // Z[k] of the M-point transform inside the row buffer (k1 = k % R1 is the row, k / R1 the row-FFT bin)
@@ -404,14 +463,14 @@ JADE_DEVICE void cta_fft(cpx* rowbuf, const cpx* s_twI, const cpx* JADE_RESTRICT
 #pragma unroll
     for (int n1 = 0; n1 < 32; ++n1) v[brev(n1, 5)] = row[lane + 32 * n1];
     __syncwarp();
-    warp_fft<32>(v, u, row, s_twI, lane);
+    warp_fft<32, false>(v, u, row, s_twI, lane);
 #pragma unroll
     for (int k2 = 0; k2 < 32; ++k2) row[lane + 32 * k2] = u[k2];
     __syncthreads();
 }
 
-template <int R1, bool MULTI, bool POOL>
-JADE_KERNEL(32 * R1) stft_cta_kernel(const KParams P)
+template <int R1, int MIXK, bool GENERAL>
+JADE_KERNEL(32 * R1, 1) stft_cta_kernel(const KParams P)
 {
     using Cfg = CtaCfg<R1>;
     constexpr int M = Cfg::M, N = Cfg::N, THREADS = Cfg::THREADS;
@@ -427,72 +486,71 @@ JADE_KERNEL(32 * R1) stft_cta_kernel(const KParams P)
     for (int i = t; i < P.npal; i += THREADS) s_pal[i] = P.palette[i];
     __syncthreads();
 
-    const long long total = (long long)P.ncols * P.nstreams;
-    const int right_ch = P.channels > 1 ? 1 : 0;
-    const float nchf = (float)P.channels;
+    const unsigned total = (unsigned)P.ncols * (unsigned)P.nstreams;
+    int ch0, ch1;
+    channel_range(P, ch0, ch1);
     const cpx* JADE_RESTRICT winp = reinterpret_cast<const cpx*>(P.window);
 
-    for (long long g = blockIdx.x; g < total; g += gridDim.x) {
-        const int stream = (int)(g / P.ncols);
-        const long long j = P.first_col + (g % P.ncols);
+    for (unsigned g = blockIdx.x; g < total; g += gridDim.x) {
+        const int stream = (int)(g / (unsigned)P.ncols);
+        const long long j = P.first_col + (g - (unsigned)stream * (unsigned)P.ncols);
         const long long st = frame_start(P, j);
         const bool fast = P.aligned2 && st >= 0 && st + N <= P.nsamples;
 
         float acc[33];
-        if (MULTI) {
 #pragma unroll
-            for (int q = 0; q < 33; ++q) mix_init(acc[q], P.mix_mode);
-        }
-        int ch0 = 0, ch1 = P.channels;
-        if (MULTI && P.mix_mode == K_MIX_LEFT) ch1 = 1;
-        if (MULTI && P.mix_mode == K_MIX_RIGHT) { ch0 = right_ch; ch1 = right_ch + 1; }
+        for (int q = 0; q < 33; ++q) acc[q] = mix_init<MIXK>(P.mix_mode);
 
         for (int ch = ch0; ch < ch1; ++ch) {
             const float* x = P.samples + stream * P.stream_stride + ch * P.channel_stride;
             const long long ns = P.nsamples;
-            cta_fft<R1>(rowbuf, s_twI, P.twA, [&](int m) {
-                const cpx z = load_pair(x, st + 2 * m, ns, fast);
-                const cpx w = winp[m];
-                return mk(z.x * w.x, z.y * w.y);
-            });
+            if (fast) {
+                const cpx* xz = reinterpret_cast<const cpx*>(x + st);
+                cta_fft<R1>(rowbuf, s_twI, P.twA, [&](int m) {
+                    const cpx z = xz[m];
+                    const cpx w = winp[m];
+                    return mk(z.x * w.x, z.y * w.y);
+                });
+            } else {
+                cta_fft<R1>(rowbuf, s_twI, P.twA, [&](int m) {
+                    const cpx z = load_pair_guarded(x, st + 2 * m, ns);
+                    const cpx w = winp[m];
+                    return mk(z.x * w.x, z.y * w.y);
+                });
+            }
 #pragma unroll
             for (int q = 0; q < 32; ++q) {
                 const int k = t + THREADS * q;
                 const cpx zk = rowbuf_get<R1>(rowbuf, k);
                 const cpx zp = rowbuf_get<R1>(rowbuf, (M - k) & (M - 1));
-                const float p = split_power(zk, zp, P.twP[k]);
-                if (MULTI) mix_add(acc[q], p, P.mix_mode, ch, right_ch);
-                else acc[q] = p;
+                mix_add<MIXK>(acc[q], split_power(zk, zp, P.twP[k]), P.mix_mode);
             }
             {
                 const cpx z0 = rowbuf[0];
-                const float p = split_power(z0, z0, P.twP[M]);
-                if (MULTI) mix_add(acc[32], p, P.mix_mode, ch, right_ch);
-                else acc[32] = p;
+                mix_add<MIXK>(acc[32], split_power(z0, z0, P.twP[M]), P.mix_mode);
             }
             __syncthreads();
-        }
-        if (MULTI) {
-#pragma unroll
-            for (int q = 0; q < 33; ++q) acc[q] = mix_done(acc[q], P.mix_mode, nchf);
         }
         const ColOut o = col_out(P, stream, j);
-        if (!POOL) {
+        if (!GENERAL) {
+            const float scale = (MIXK == MIX_SUM) ? (1.0f / (float)P.channels) : 1.0f;
 #pragma unroll
-            for (int q = 0; q < 32; ++q) emit_bin(P, s_pal, o, t + THREADS * q, acc[q]);
-            if (t == 0) emit_bin(P, s_pal, o, M, acc[32]);
+            for (int q = 0; q < 33; ++q) {
+                if (q == 32 && t != 0) break;
+                const int k = t + THREADS * q;
+                const float d = to_db_fast(MIXK == MIX_SUM ? acc[q] * scale : acc[q]);
+                const uint32_t c = colour_of(d, P, s_pal);
+                if (o.db) o.db[k] = d;
+                if (o.pix) o.pix[P.flip ? M - k : k] = c;
+            }
         } else {
 #pragma unroll
-            for (int q = 0; q < 32; ++q) {
-                spec[t + THREADS * q] = acc[q];
-                if (o.db) o.db[t + THREADS * q] = to_db(acc[q], P.db_precise);
-            }
-            if (t == 0) {
-                spec[M] = acc[32];
-                if (o.db) o.db[M] = to_db(acc[32], P.db_precise);
-            }
+            for (int q = 0; q < 32; ++q) spec[t + THREADS * q] = acc[q];
+            if (t == 0) spec[M] = acc[32];
             __syncthreads();
-            emit_pooled(P, s_pal, o, spec, t, THREADS);
+            emit_general_bins(P, s_pal, o, spec, t, THREADS);
+            __syncthreads();
+            emit_general_rows(P, s_pal, o, spec, t, THREADS);
             __syncthreads();
         }
     }
@@ -503,10 +561,10 @@ JADE_KERNEL(32 * R1) stft_cta_kernel(const KParams P)
 //   X[k] = E[k] + W_N^k O[k],  X[N/2-k] = conj(E[k] - W_N^k O[k]),  k = 0..N/4
 // E / O = real FFT (size N/2, M2 = N/4 = 1024*R1 complex points) of the even / odd windowed samples.
 // The complex working set of one half (8*M2 bytes) fits in shared memory; E and the mixed power spectrum go
-// through an L2-resident per-CTA scratch slot.
+// through an L2-resident per-CTA scratch slot; the epilogue is the general one.
 // =========================================================================================================
-template <int R1, bool MULTI>
-JADE_KERNEL(32 * R1) stft_cta2_kernel(const KParams P)
+template <int R1, int MIXK>
+JADE_KERNEL(32 * R1, 1) stft_cta2_kernel(const KParams P)
 {
     using Cfg = CtaCfg<R1>;
     constexpr int M2 = Cfg::M;      // complex points per half
@@ -526,18 +584,15 @@ JADE_KERNEL(32 * R1) stft_cta2_kernel(const KParams P)
 
     cpx* se = P.scratch_e + (long long)blockIdx.x * (M2 + 1);
     float* sp = P.scratch_p + (long long)blockIdx.x * (NH + 1);
-    const long long total = (long long)P.ncols * P.nstreams;
-    const int right_ch = P.channels > 1 ? 1 : 0;
-    const float nchf = (float)P.channels;
+    const unsigned total = (unsigned)P.ncols * (unsigned)P.nstreams;
+    int ch0, ch1;
+    channel_range(P, ch0, ch1);
 
-    for (long long g = blockIdx.x; g < total; g += gridDim.x) {
-        const int stream = (int)(g / P.ncols);
-        const long long j = P.first_col + (g % P.ncols);
+    for (unsigned g = blockIdx.x; g < total; g += gridDim.x) {
+        const int stream = (int)(g / (unsigned)P.ncols);
+        const long long j = P.first_col + (g - (unsigned)stream * (unsigned)P.ncols);
         const long long st = frame_start(P, j);
         const bool fast = st >= 0 && st + N <= P.nsamples;
-        int ch0 = 0, ch1 = P.channels;
-        if (MULTI && P.mix_mode == K_MIX_LEFT) ch1 = 1;
-        if (MULTI && P.mix_mode == K_MIX_RIGHT) { ch0 = right_ch; ch1 = right_ch + 1; }
 
         for (int ch = ch0; ch < ch1; ++ch) {
             const float* x = P.samples + stream * P.stream_stride + ch * P.channel_stride;
@@ -563,35 +618,24 @@ JADE_KERNEL(32 * R1) stft_cta2_kernel(const KParams P)
                         const float ar = e.x + q.x, ai = e.y + q.y, br = e.x - q.x, bi = e.y - q.y;
                         const float p1 = fm(ar, ar, ai * ai), p2 = fm(br, br, bi * bi);
                         const int k2 = NH - k;
-                        if (!MULTI) {
-                            sp[k] = p1;
-                            sp[k2] = p2;
-                        } else {
-                            float a1, a2;
-                            if (ch == ch0) { mix_init(a1, P.mix_mode); mix_init(a2, P.mix_mode); }
-                            else { a1 = sp[k]; a2 = sp[k2]; }
-                            mix_add(a1, p1, P.mix_mode, ch, right_ch);
-                            mix_add(a2, p2, P.mix_mode, ch, right_ch);
-                            sp[k] = a1;
-                            if (k2 != k) sp[k2] = a2;
+                        float a1 = mix_init<MIXK>(P.mix_mode), a2 = a1;
+                        if (MIXK != MIX_NONE && ch != ch0) {
+                            a1 = sp[k];
+                            a2 = sp[k2];
                         }
+                        mix_add<MIXK>(a1, p1, P.mix_mode);
+                        mix_add<MIXK>(a2, p2, P.mix_mode);
+                        sp[k] = a1;
+                        if (k2 != k) sp[k2] = a2;
                     }
                 }
                 __syncthreads();
             }
         }
         const ColOut o = col_out(P, stream, j);
-        if (MULTI) {
-            for (int k = t; k <= NH; k += THREADS) sp[k] = mix_done(sp[k], P.mix_mode, nchf);
-            __syncthreads();
-        }
-        if (!P.pooled) {
-            for (int k = t; k <= NH; k += THREADS) emit_bin(P, s_pal, o, k, sp[k]);
-        } else {
-            if (o.db)
-                for (int k = t; k <= NH; k += THREADS) o.db[k] = to_db(sp[k], P.db_precise);
-            emit_pooled(P, s_pal, o, sp, t, THREADS);
-        }
+        emit_general_bins(P, s_pal, o, sp, t, THREADS);
+        __syncthreads();
+        emit_general_rows(P, s_pal, o, sp, t, THREADS);
         __syncthreads();
     }
 }

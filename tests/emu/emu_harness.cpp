@@ -16,24 +16,26 @@ using jade::KParams;
 
 namespace {
 template <int T>
-void run_warp(const KParams& P, bool multi, bool pool, int grid)
+void run_warp(const KParams& P, int mixk, bool general, int grid)
 {
-    const int smem = jade::WarpCfg<T>::smem_bytes(P.npal, pool);
+    const int smem = jade::WarpCfg<T>::smem_bytes(P.npal, general);
     const int block = jade::WARP_KERNEL_WARPS * 32;
-    if (multi && pool) jade_emu::launch(jade::stft_warp_kernel<T, true, true>, grid, block, smem, P);
-    else if (multi) jade_emu::launch(jade::stft_warp_kernel<T, true, false>, grid, block, smem, P);
-    else if (pool) jade_emu::launch(jade::stft_warp_kernel<T, false, true>, grid, block, smem, P);
-    else jade_emu::launch(jade::stft_warp_kernel<T, false, false>, grid, block, smem, P);
+    if (mixk == jade::MIX_SEL) jade_emu::launch(jade::stft_warp_kernel<T, jade::MIX_SEL, true>, grid, block, smem, P);
+    else if (mixk == jade::MIX_SUM && general) jade_emu::launch(jade::stft_warp_kernel<T, jade::MIX_SUM, true>, grid, block, smem, P);
+    else if (mixk == jade::MIX_SUM) jade_emu::launch(jade::stft_warp_kernel<T, jade::MIX_SUM, false>, grid, block, smem, P);
+    else if (general) jade_emu::launch(jade::stft_warp_kernel<T, jade::MIX_NONE, true>, grid, block, smem, P);
+    else jade_emu::launch(jade::stft_warp_kernel<T, jade::MIX_NONE, false>, grid, block, smem, P);
 }
 template <int R1>
-void run_cta(const KParams& P, bool multi, bool pool, int grid)
+void run_cta(const KParams& P, int mixk, bool general, int grid)
 {
-    const int smem = jade::CtaCfg<R1>::smem_bytes(P.npal, pool);
+    const int smem = jade::CtaCfg<R1>::smem_bytes(P.npal, general);
     const int block = 32 * R1;
-    if (multi && pool) jade_emu::launch(jade::stft_cta_kernel<R1, true, true>, grid, block, smem, P);
-    else if (multi) jade_emu::launch(jade::stft_cta_kernel<R1, true, false>, grid, block, smem, P);
-    else if (pool) jade_emu::launch(jade::stft_cta_kernel<R1, false, true>, grid, block, smem, P);
-    else jade_emu::launch(jade::stft_cta_kernel<R1, false, false>, grid, block, smem, P);
+    if (mixk == jade::MIX_SEL) jade_emu::launch(jade::stft_cta_kernel<R1, jade::MIX_SEL, true>, grid, block, smem, P);
+    else if (mixk == jade::MIX_SUM && general) jade_emu::launch(jade::stft_cta_kernel<R1, jade::MIX_SUM, true>, grid, block, smem, P);
+    else if (mixk == jade::MIX_SUM) jade_emu::launch(jade::stft_cta_kernel<R1, jade::MIX_SUM, false>, grid, block, smem, P);
+    else if (general) jade_emu::launch(jade::stft_cta_kernel<R1, jade::MIX_NONE, true>, grid, block, smem, P);
+    else jade_emu::launch(jade::stft_cta_kernel<R1, jade::MIX_NONE, false>, grid, block, smem, P);
 }
 } // namespace
 
@@ -72,7 +74,13 @@ extern "C" int emu_render(const jade_config* cin, const int32_t* palette, int np
         R = c.rows;
         pooled = true;
     }
-    const bool multi = c.channels > 1 || c.mix_mode == JADE_MIX_MIN;
+    const int contributing = (c.mix_mode == JADE_MIX_LEFT || c.mix_mode == JADE_MIX_RIGHT) ? 1 : c.channels;
+    int multi = jade::MIX_NONE;
+    if (c.mix_mode == JADE_MIX_MIN || (c.mix_mode == JADE_MIX_MAX && contributing > 1)) multi = jade::MIX_SEL;
+    else if (c.mix_mode == JADE_MIX_ABSMEAN && contributing > 1) multi = jade::MIX_SUM;
+    const bool pow2ch = (c.channels & (c.channels - 1)) == 0;
+    const bool general = pooled || c.row_map != JADE_ROWS_IDENTITY || c.db_precise != 0 || multi == jade::MIX_SEL ||
+                         (multi == jade::MIX_SUM && !pow2ch);
     std::vector<jade_host::cpxf> twP, twI, twA, twH;
     jade_host::twiddles(N, M + 1, 1, twP);
     KParams P;
@@ -104,12 +112,12 @@ extern "C" int emu_render(const jade_config* cin, const int32_t* palette, int np
         jade_host::twiddle_matrix(32 * T, 32, T, twI);
         P.twI = reinterpret_cast<const jade::cpx*>(twI.data());
         switch (T) {
-        case 1: run_warp<1>(P, multi, pooled, grid); break;
-        case 2: run_warp<2>(P, multi, pooled, grid); break;
-        case 4: run_warp<4>(P, multi, pooled, grid); break;
-        case 8: run_warp<8>(P, multi, pooled, grid); break;
-        case 16: run_warp<16>(P, multi, pooled, grid); break;
-        case 32: run_warp<32>(P, multi, pooled, grid); break;
+        case 1: run_warp<1>(P, multi, general, grid); break;
+        case 2: run_warp<2>(P, multi, general, grid); break;
+        case 4: run_warp<4>(P, multi, general, grid); break;
+        case 8: run_warp<8>(P, multi, general, grid); break;
+        case 16: run_warp<16>(P, multi, general, grid); break;
+        case 32: run_warp<32>(P, multi, general, grid); break;
         default: return -1;
         }
     } else {
@@ -127,14 +135,15 @@ extern "C" int emu_render(const jade_config* cin, const int32_t* palette, int np
             P.scratch_e = se.data();
             P.scratch_p = sp.data();
             const int smem = jade::CtaCfg<16>::smem_bytes(npal, false);
-            if (multi) jade_emu::launch(jade::stft_cta2_kernel<16, true>, grid, 512, smem, P);
-            else jade_emu::launch(jade::stft_cta2_kernel<16, false>, grid, 512, smem, P);
+            if (multi == jade::MIX_SEL) jade_emu::launch(jade::stft_cta2_kernel<16, jade::MIX_SEL>, grid, 512, smem, P);
+            else if (multi == jade::MIX_SUM) jade_emu::launch(jade::stft_cta2_kernel<16, jade::MIX_SUM>, grid, 512, smem, P);
+            else jade_emu::launch(jade::stft_cta2_kernel<16, jade::MIX_NONE>, grid, 512, smem, P);
         } else {
             switch (R1) {
-            case 2: run_cta<2>(P, multi, pooled, grid); break;
-            case 4: run_cta<4>(P, multi, pooled, grid); break;
-            case 8: run_cta<8>(P, multi, pooled, grid); break;
-            case 16: run_cta<16>(P, multi, pooled, grid); break;
+            case 2: run_cta<2>(P, multi, general, grid); break;
+            case 4: run_cta<4>(P, multi, general, grid); break;
+            case 8: run_cta<8>(P, multi, general, grid); break;
+            case 16: run_cta<16>(P, multi, general, grid); break;
             default: return -1;
             }
         }
