@@ -101,6 +101,8 @@ int jade_get_config(jade_engine* e, jade_config* out);    /* resolved values */
 int jade_set_pause(jade_engine* e, int on);
 int jade_set_window(jade_engine* e, int window);          /* like setWindow: table only, no buffer reset */
 int jade_get_window(jade_engine* e, float* out, int n);   /* the unit-RMS window table (Spectrogram.cpp:239-293) */
+/* the same table without an engine (host-only, works without a GPU): Spectrogram::setWindowFkt for `window`, length n */
+int jade_window_build(int window, int n, float* out);
 int jade_reset(jade_engine* e);                           /* buildmem() without reconfiguration */
 
 /* ---- palette ---- */

@@ -54,6 +54,7 @@ SYMBOLS = {
     "jade_set_pause": (_I, [_P, _I]),
     "jade_set_window": (_I, [_P, _I]),
     "jade_get_window": (_I, [_P, _P, _I]),
+    "jade_window_build": (_I, [_I, _I, _P]),
     "jade_reset": (_I, [_P]),
     "jade_palette_build": (_I, [_I, _I, _I, _P]),
     "jade_set_palette": (_I, [_P, _P, _I]),

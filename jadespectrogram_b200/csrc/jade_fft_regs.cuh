@@ -18,7 +18,7 @@
 
 namespace jade {
 
-struct cpx {
+struct alignas(8) cpx { // 8-byte aligned so that loads/stores are single 64-bit accesses (LDG.64 / LDS.64)
     float x, y;
 };
 

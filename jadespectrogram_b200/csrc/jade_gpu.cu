@@ -549,7 +549,7 @@ int jade_configure(jade_engine* e, const jade_config* cin)
         else if (c.mix_mode == JADE_MIX_ABSMEAN && contributing > 1) e->mixk = jade::MIX_SUM;
         else e->mixk = jade::MIX_NONE;
         const bool pow2ch = (c.channels & (c.channels - 1)) == 0;
-        e->general = e->pooled || c.row_map != JADE_ROWS_IDENTITY || c.db_precise != 0 || e->mixk == jade::MIX_SEL ||
+        e->general = e->pooled || c.row_map != JADE_ROWS_IDENTITY || c.db_precise != 0 || c.flip_y == 0 || e->mixk == jade::MIX_SEL ||
                      (e->mixk == jade::MIX_SUM && !pow2ch);
     }
 
@@ -630,6 +630,15 @@ int jade_get_window(jade_engine* e, float* out, int n)
     if (!e->configured) return fail(e, JADE_ERR_STATE, "engine not configured");
     if (n != e->N) return fail(e, JADE_ERR_ARG, "window length %d != fft_size %d", n, e->N);
     memcpy(out, e->h_window.data(), (size_t)n * 4);
+    return JADE_OK;
+}
+
+int jade_window_build(int window, int n, float* out)
+{
+    if (!out || n < 1 || window < 0 || window > JADE_WIN_HANNPOISSON) return JADE_ERR_ARG;
+    std::vector<float> w;
+    jade_host::make_window(window, n, w);
+    memcpy(out, w.data(), (size_t)n * 4);
     return JADE_OK;
 }
 

@@ -7,7 +7,7 @@
 
 namespace jade_host {
 
-struct cpxf {
+struct alignas(8) cpxf {
     float x, y;
 };
 

@@ -36,7 +36,14 @@
 #define JADE_KERNEL(...) __global__ void __launch_bounds__(__VA_ARGS__)
 #define JADE_DYN_SMEM(name) extern __shared__ float4 name[]
 #define JADE_RESTRICT __restrict__
-#define JADE_LOG2F(x) __log2f(x)
+// raw MUFU.LG2: the argument is p + 1e-11 >= 1e-11, never denormal, so __log2f's denormal pre-scaling is dead weight
+__device__ __forceinline__ float jade_lg2(float x)
+{
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+#define JADE_LOG2F(x) jade_lg2(x)
 #define JADE_FDIV(a, b) __fdiv_rn((a), (b))
 #endif
 
@@ -111,12 +118,11 @@ JADE_DEVICE float to_db(float p, int precise) { return precise ? to_db_precise(p
 // (the reference would read out of bounds when m_Min > m_Max).
 JADE_DEVICE uint32_t colour_of(float v, const KParams& P, const uint32_t* pal)
 {
-    if (v >= P.pmax) v = P.pmaxc;
-    if (v < P.pmin) v = P.pmin;
+    v = (v >= P.pmax) ? P.pmaxc : v;
+    v = fmaxf(v, P.pmin);            // == `if (v < m_Min) v = m_Min` for every non-NaN v
     const float d = v - P.pmin;
     int idx = (int)(d * P.pmult);
-    idx = idx < P.npal ? idx : P.npal - 1;
-    idx = idx < 0 ? 0 : idx;
+    idx = max(min(idx, P.npal - 1), 0);
     return pal[idx];
 }
 
@@ -291,8 +297,8 @@ struct WarpCfg {
     }
 };
 
-// GENERAL = false: headline path (identity rows, hardware log2, exact reciprocal for the mean); all addressing is
-//                  base + immediate.  GENERAL = true: every other option through emit_general.
+// GENERAL = false: headline path (identity rows in the reference orientation, hardware log2, exact reciprocal for the
+//                  mean); all addressing is base + immediate.  GENERAL = true: every other option (emit_general_*).
 template <int T, int MIXK, bool GENERAL>
 JADE_KERNEL(WARP_KERNEL_WARPS * 32, (T >= 4 && !GENERAL) ? 2 : 1) stft_warp_kernel(const KParams P)
 {
@@ -349,7 +355,7 @@ JADE_KERNEL(WARP_KERNEL_WARPS * 32, (T >= 4 && !GENERAL) ? 2 : 1) stft_warp_kern
 #pragma unroll
         for (int q = 0; q < 33; ++q) acc[q] = mix_init<MIXK>(P.mix_mode);
 
-        for (int ch = ch0; ch < ch1; ++ch) {
+        for (int ch = ch0; ch < (MIXK == MIX_NONE ? ch0 + 1 : ch1); ++ch) {
             const float* x = P.samples + stream * P.stream_stride + ch * P.channel_stride;
             cpx v[32], u[32];
             if (fast) {
@@ -390,16 +396,16 @@ JADE_KERNEL(WARP_KERNEL_WARPS * 32, (T >= 4 && !GENERAL) ? 2 : 1) stft_warp_kern
         if (!GENERAL) {
             // identity rows: bin k = s + T*q -> row (flip ? M - k : k); mean over 2^n channels is an exact multiply
             const float scale = (MIXK == MIX_SUM) ? (1.0f / (float)P.channels) : 1.0f;
-            uint32_t* prow = o.pix ? (P.flip ? o.pix + (M - s) : o.pix + s) : nullptr;
+            // reference orientation (flip): bin k = s + T*q lands in row M - k; every store is base + immediate
+            uint32_t* prow = o.pix ? o.pix + (M - s) : nullptr;
             float* drow = o.db ? o.db + s : nullptr;
-            const int pstep = P.flip ? -T : T;
 #pragma unroll
             for (int q = 0; q < 33; ++q) {
                 if (q == 32 && s != 0) break;
                 const float d = to_db_fast(MIXK == MIX_SUM ? acc[q] * scale : acc[q]);
                 const uint32_t c = colour_of(d, P, s_pal);
                 if (drow) drow[T * q] = d;
-                if (prow) prow[pstep * q] = c;
+                if (prow) prow[-T * q] = c;
             }
         } else {
 #pragma unroll
@@ -501,7 +507,7 @@ JADE_KERNEL(32 * R1, 1) stft_cta_kernel(const KParams P)
 #pragma unroll
         for (int q = 0; q < 33; ++q) acc[q] = mix_init<MIXK>(P.mix_mode);
 
-        for (int ch = ch0; ch < ch1; ++ch) {
+        for (int ch = ch0; ch < (MIXK == MIX_NONE ? ch0 + 1 : ch1); ++ch) {
             const float* x = P.samples + stream * P.stream_stride + ch * P.channel_stride;
             const long long ns = P.nsamples;
             if (fast) {
@@ -541,7 +547,7 @@ JADE_KERNEL(32 * R1, 1) stft_cta_kernel(const KParams P)
                 const float d = to_db_fast(MIXK == MIX_SUM ? acc[q] * scale : acc[q]);
                 const uint32_t c = colour_of(d, P, s_pal);
                 if (o.db) o.db[k] = d;
-                if (o.pix) o.pix[P.flip ? M - k : k] = c;
+                if (o.pix) o.pix[M - k] = c;
             }
         } else {
 #pragma unroll
@@ -594,7 +600,7 @@ JADE_KERNEL(32 * R1, 1) stft_cta2_kernel(const KParams P)
         const long long st = frame_start(P, j);
         const bool fast = st >= 0 && st + N <= P.nsamples;
 
-        for (int ch = ch0; ch < ch1; ++ch) {
+        for (int ch = ch0; ch < (MIXK == MIX_NONE ? ch0 + 1 : ch1); ++ch) {
             const float* x = P.samples + stream * P.stream_stride + ch * P.channel_stride;
             const long long ns = P.nsamples;
             const float* JADE_RESTRICT win = P.window;

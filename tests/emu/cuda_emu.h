@@ -36,6 +36,8 @@ inline void* dyn_smem() { return g_block->smem.data(); }
 
 inline void __syncthreads() { pthread_barrier_wait(&jade_emu::g_block->block_bar); }
 inline void __syncwarp(unsigned = 0xffffffffu) { pthread_barrier_wait(&jade_emu::g_block->warp_bar[threadIdx.x >> 5]); }
+inline int max(int a, int b) { return a > b ? a : b; }
+inline int min(int a, int b) { return a < b ? a : b; }
 inline float sinpif(float x) { return (float)std::sin(M_PI * (double)x); }
 
 namespace jade_emu {

@@ -79,7 +79,7 @@ extern "C" int emu_render(const jade_config* cin, const int32_t* palette, int np
     if (c.mix_mode == JADE_MIX_MIN || (c.mix_mode == JADE_MIX_MAX && contributing > 1)) multi = jade::MIX_SEL;
     else if (c.mix_mode == JADE_MIX_ABSMEAN && contributing > 1) multi = jade::MIX_SUM;
     const bool pow2ch = (c.channels & (c.channels - 1)) == 0;
-    const bool general = pooled || c.row_map != JADE_ROWS_IDENTITY || c.db_precise != 0 || multi == jade::MIX_SEL ||
+    const bool general = pooled || c.row_map != JADE_ROWS_IDENTITY || c.db_precise != 0 || c.flip_y == 0 || multi == jade::MIX_SEL ||
                          (multi == jade::MIX_SUM && !pow2ch);
     std::vector<jade_host::cpxf> twP, twI, twA, twH;
     jade_host::twiddles(N, M + 1, 1, twP);

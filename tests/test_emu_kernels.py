@@ -1,0 +1,76 @@
+"""Kernel logic on the CPU SIMT emulator (tests/emu): the product's kernel source (jade_kernels.cuh) compiled with
+-DJADE_EMU and executed with one OS thread per CUDA thread, against the oracle.  This is a debugging aid for the
+GPU-less build container -- it proves index arithmetic, shared-memory layouts and barriers, not performance -- and it is
+not a product path (the product library contains no host implementation of these kernels)."""
+import numpy as np
+import pytest
+
+import emu_lib as E
+import oracle_lib as O
+import parity
+import signals
+from jadespectrogram_b200._capi import MIX, ROWS, WIN, JadeConfig
+
+pytestmark = pytest.mark.timeout(300)
+
+
+def _cfg(N, hop, ch, window, mix, **kw):
+    c = JadeConfig()
+    c.sample_rate = 48000.0
+    c.fft_size, c.hop, c.frames_per_block, c.block_stride, c.preroll = N, hop, 1, hop, -1
+    c.window, c.channels, c.mix_mode = WIN[window], ch, MIX[mix]
+    c.row_map, c.flip_y, c.power_scale = 0, 1, 1.0
+    for k, v in kw.items():
+        setattr(c, k, v)
+    return c
+
+
+CASES = [(64, 16, 1, "rect", "absmean"), (128, 32, 2, "hann", "absmean"), (256, 64, 1, "hamming", "absmean"),
+         (512, 128, 3, "flattop", "absmean"), (1024, 512, 1, "hann", "absmean"), (2048, 512, 2, "hann", "absmean"),
+         (2048, 256, 1, "hann", "min"), (1024, 205, 2, "hannpoisson", "max"), (2048, 512, 2, "hann", "right"),
+         (4096, 1024, 1, "hann", "absmean"), (16384, 4096, 1, "blackmanharris", "absmean"), (65536, 8192, 1, "hann", "absmean")]
+
+
+@pytest.mark.parametrize("N,hop,ch,window,mix", CASES)
+def test_emulated_kernels_match_oracle(N, hop, ch, window, mix):
+    ncols = 9 if N <= 2048 else 3
+    x = signals.streams(2 if N <= 2048 else 1, ch, hop * (ncols - 1) + 64, 48000.0)
+    pal = O.Palette(256, O.PAL["jade"]).table()
+    db, pix = E.render(_cfg(N, hop, ch, window, mix), pal, -50.0, 50.0, x, 0, ncols, N // 2 + 1, grid=2)
+    for s in range(x.shape[0]):
+        odb, opix = O.render_batch(x[s], fft_size=N, hop=hop, window=window, mix=mix, ncols=ncols)
+        parity.check_db(db[s], odb, N, f"stream {s}")
+        parity.check_pixels(pix[s], opix, odb[:, ::-1], -50.0, 50.0, 256, f"stream {s}")
+
+
+def test_emulated_general_epilogue_options():
+    N, hop = 1024, 256
+    x = signals.streams(1, 2, hop * 8, 48000.0)
+    pal = O.Palette(64, O.PAL["viridis"]).table()
+    odb, _ = O.render_batch(x[0], fft_size=N, hop=hop, ncols=8)
+    # precise dB reproduces the oracle's double log10 on identical power up to float FFT differences; un-flipped rows
+    db, pix = E.render(_cfg(N, hop, 2, "hann", "absmean", db_precise=1, flip_y=0), pal, -80.0, 0.0, x, 0, 8, N // 2 + 1)
+    parity.check_db(db[0], odb, N)
+    ref = O.Palette(64, O.PAL["viridis"])
+    ref.set_value_range(-80.0, 0.0)
+    parity.check_pixels(pix[0], ref.lookup(odb).astype(np.uint32) | np.uint32(0xFF000000), odb, -80.0, 0.0, 64)
+    # linear crop: rows are the bins the reference's paint() would show
+    c = _cfg(N, hop, 2, "hann", "absmean", row_map=ROWS["linear_crop"], fmin=1000.0, fmax=8000.0)
+    lo, hi = 43, 171  # int(2*8000/48000*513+.5)=171 ; interval=int(171.0-21.375+.5)=150 -> lo = 21? computed below
+    from jadespectrogram_b200 import _capi
+    import ctypes as C
+    a, b = C.c_int(), C.c_int()
+    _capi.load().jade_linear_crop(48000.0, N // 2 + 1, 1000.0, 8000.0, C.byref(a), C.byref(b))
+    lo, hi = a.value, b.value
+    db, pix = E.render(c, pal, -80.0, 0.0, x, 0, 8, hi - lo)
+    full = ref.lookup(odb).astype(np.uint32) | np.uint32(0xFF000000)
+    parity.check_pixels(pix[0], full[:, lo:hi][:, ::-1], odb[:, lo:hi][:, ::-1], -80.0, 0.0, 64)
+    # log max-pool rows: dB of the band maximum
+    R = 40
+    c = _cfg(N, hop, 2, "hann", "absmean", row_map=ROWS["log_maxpool"], rows=R, fmin=50.0, fmax=20000.0)
+    blo, bhi = np.zeros(R, np.int32), np.zeros(R, np.int32)
+    _capi.load().jade_log_rows(48000.0, N, R, 50.0, 20000.0, blo.ctypes.data, bhi.ctypes.data)
+    db, pix = E.render(c, pal, -80.0, 0.0, x, 0, 8, R)
+    pooled = np.stack([odb[:, blo[r]:bhi[r]].max(axis=1) for r in range(R)], axis=1)
+    parity.check_pixels(pix[0], (ref.lookup(pooled).astype(np.uint32) | np.uint32(0xFF000000))[:, ::-1], pooled[:, ::-1],
+                        -80.0, 0.0, 64)

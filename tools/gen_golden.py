@@ -1,0 +1,107 @@
+#!/usr/bin/env python3
+"""Generate the committed golden fixtures under tests/golden/ (run in the build container, where /root/reference exists).
+
+  palette_ref.npz  -- colour tables and lookup sweeps produced by the REFERENCE's own CColorpalette.cpp compiled in place
+                      (oracle/_ref/libjade_ref.so): 7 schemes x {2,3,7,64,255,256,1024} colours x invert {0,1}, plus
+                      getRGBColor sweeps over several value ranges (incl. >=max, <min, max<=0, equal bounds).
+  windows.npz      -- the six unit-RMS window tables at N = 64 and 2048 from the oracle restatement of setWindowFkt
+                      (Spectrogram.cpp:239-293), and sha256 digests at N = 65536.
+  pipeline.npz     -- seeded inputs with the oracle's dB columns and ARGB pixels for small end-to-end cases.
+
+    python tools/gen_golden.py
+"""
+import hashlib
+import pathlib
+import sys
+
+import numpy as np
+
+ROOT = pathlib.Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+import oracle_lib as O  # noqa: E402
+import signals  # noqa: E402
+
+OUT = ROOT / "tests" / "golden"
+OUT.mkdir(exist_ok=True)
+
+SIZES = (2, 3, 7, 64, 255, 256, 1024)
+RANGES = [(-50.0, 50.0), (0.0, 1.0), (-120.0, -20.0), (-80.0, 0.0), (10.0, -10.0), (-30.0, -30.0), (5.0, 5.0), (0.0, 0.0)]
+
+
+def sweep_values(mn, mx):
+    lo, hi = min(mn, mx), max(mn, mx)
+    span = max(hi - lo, 1.0)
+    v = np.linspace(lo - 0.25 * span, hi + 0.25 * span, 4001).astype(np.float32)
+    extra = np.array([lo, hi, np.nextafter(np.float32(hi), np.float32(-1e9)), np.float32(hi) * np.float32(0.9999), -1e30, 1e30],
+                     np.float32)
+    return np.concatenate([v, extra])
+
+
+def palettes():
+    assert O.ref() is not None, "oracle/_ref/libjade_ref.so missing: run `make -C oracle` where /root/reference exists"
+    out = {}
+    for scheme in range(7):
+        for n in SIZES:
+            for inv in (0, 1):
+                p = O.Palette(n, scheme, use_ref=True)
+                if inv:
+                    p.set_invert(1)
+                    p.set_color_scheme(scheme)
+                out[f"table_s{scheme}_n{n}_i{inv}"] = p.table().astype(np.int32)
+    # stale-entry quirk: kMono+invert after another scheme keeps the upper half of the previous table
+    p = O.Palette(256, 6, use_ref=True)
+    p.set_invert(1)
+    p.set_color_scheme(0)
+    out["table_jade_then_mono_inverted_n256"] = p.table().astype(np.int32)
+    p = O.Palette(None, None, use_ref=True)
+    out["table_default_ctor"] = p.table().astype(np.int32)
+    for i, (mn, mx) in enumerate(RANGES):
+        for n, scheme in ((256, 6), (64, 4), (7, 3)):
+            p = O.Palette(n, scheme, use_ref=True)
+            p.set_value_range(mn, mx)
+            v = sweep_values(mn, mx)
+            # the reference's own range rules (CColorpalette.cpp:39-54); m_Min >= m_Max (equal non-positive bounds) makes
+            # its index negative / NaN, i.e. an out-of-bounds read: those ranges have no defined reference output
+            a, b = np.float32(min(mn, mx)), np.float32(max(mn, mx))
+            if a == b:
+                a = np.float32(0.99 * float(b))
+            if not (b > a):
+                continue
+            out[f"sweep_values_r{i}_n{n}_s{scheme}"] = v
+            out[f"sweep_colors_r{i}_n{n}_s{scheme}"] = p.lookup(v).astype(np.int32)
+    np.savez_compressed(OUT / "palette_ref.npz", **out)
+    print("palette_ref.npz", len(out), "arrays")
+
+
+def windows():
+    out = {}
+    for name in O.WIN:
+        for n in (64, 2048):
+            out[f"{name}_{n}"] = O.window(name, n)
+        out[f"{name}_65536_sha256"] = np.frombuffer(hashlib.sha256(O.window(name, 65536).tobytes()).digest(), np.uint8)
+    np.savez_compressed(OUT / "windows.npz", **out)
+    print("windows.npz", len(out), "arrays")
+
+
+def pipeline():
+    out = {}
+    cases = [("n64_mono", 64, 16, 1, "hann", "absmean"), ("n256_stereo", 256, 64, 2, "blackmanharris", "absmean"),
+             ("n1024_cfg1", 1024, 512, 1, "hann", "absmean"), ("n2048_cfg2", 2048, 512, 2, "hann", "absmean"),
+             ("n512_max3", 512, 128, 3, "hamming", "max")]
+    for name, N, hop, ch, win, mix in cases:
+        ncols = 12
+        x = signals.streams(1, ch, hop * ncols, 48000.0, kind="mix", seed=7 + N)[0]
+        db, pix = O.render_batch(x, fft_size=N, hop=hop, window=win, mix=mix, ncols=ncols + 1)
+        out[name + "_x"] = x
+        out[name + "_db"] = db
+        out[name + "_pix"] = pix
+        out[name + "_cfg"] = np.array([N, hop, ch, O.WIN[win], O.MIX[mix]], np.int32)
+    np.savez_compressed(OUT / "pipeline.npz", **out)
+    print("pipeline.npz", len(out), "arrays")
+
+
+if __name__ == "__main__":
+    palettes()
+    windows()
+    pipeline()
