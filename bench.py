@@ -103,28 +103,48 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(top), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_baseline(sample_seconds=12.0, threads=None):
-    """The oracle port (restated Spectrogram loop + FFT stand-in + restated palette) on the host cores."""
+def _cpu_runner():
+    """(callable(nstreams, threads) -> (frames/s, frames), kind, description).  Prefers the reference's own classes
+    compiled in place (oracle/_ref/libjade_ref.so: Spectrogram.cpp + CColorpalette.cpp against the stub JUCE/TGM headers,
+    FFT = the oracle's stand-in for the absent TGM `spectrum`); falls back to the restated oracle port."""
     import ctypes as C
 
-    import numpy as np
     import oracle_lib as O
     import signals
-    threads = threads or os.cpu_count() or 1
-    cfg = O.BatchCfg(FS, N_FFT, HOP, O.WIN["hann"], CHANNELS, O.MIX["absmean"], O.PAL["jade"], 256, 0, -50.0, 50.0, 0)
     x = signals.streams(1, CHANNELS, int(FS * 2.0), FS, kind="mix")[0]
-    frames = C.c_long(0)
-    # calibrate on one thread, then size the sample for ~sample_seconds of wall time on all threads
+    flat = x.reshape(-1)
+    if O.have_ref_spec():
+        R = O.ref()
+
+        def run(nstreams, threads):
+            frames = C.c_long(0)
+            fps = R.jr_bench_batch(FS, N_FFT, O.FEED["p25"], O.WIN["hann"], CHANNELS, O.PAL["jade"], 256, -50.0, 50.0, flat,
+                                   x.shape[1], nstreams, threads, C.byref(frames))
+            return fps, frames.value
+        return run, "reference", ("the reference's own Spectrogram::processSynchronBlock + getMem + CColorPalette::getRGBColor "
+                                  "(Spectrogram.cpp / CColorpalette.cpp compiled in place; FFT = oracle stand-in for the "
+                                  "absent TGM spectrum class), one instance per host thread, perc25 feed = hop 512")
+    cfg = O.BatchCfg(FS, N_FFT, HOP, O.WIN["hann"], CHANNELS, O.MIX["absmean"], O.PAL["jade"], 256, 0, -50.0, 50.0, 0)
+
+    def run(nstreams, threads):
+        frames = C.c_long(0)
+        fps = O.lib().jo_bench_batch(C.byref(cfg), flat, x.shape[1], nstreams, threads, C.byref(frames))
+        return fps, frames.value
+    return run, "port", "oracle port (restated Spectrogram.cpp loop, radix-2 FFT stand-in, restated palette)"
+
+
+def cpu_baseline(sample_seconds=12.0, threads=None):
+    """The reference's CPU path on the host cores, on a bounded sample of the bench workload."""
+    threads = threads or os.cpu_count() or 1
+    run, kind, what = _cpu_runner()
     t0 = time.time()
-    fps1 = O.lib().jo_bench_batch(C.byref(cfg), x.reshape(-1), x.shape[1], 1, 1, C.byref(frames))
+    fps1, per_stream = run(1, 1)  # calibrate on one thread, then size the sample for ~sample_seconds on all threads
     cal = time.time() - t0
-    per_stream = frames.value
-    nstreams = max(threads, int(sample_seconds * fps1 * threads / per_stream))
+    nstreams = max(threads, int(sample_seconds * fps1 * threads / max(per_stream, 1)))
     nstreams = (nstreams + threads - 1) // threads * threads
-    fps = O.lib().jo_bench_batch(C.byref(cfg), x.reshape(-1), x.shape[1], nstreams, threads, C.byref(frames))
-    return dict(value=fps, unit="frames/s", cores=threads, kind="port",
-                sample=f"{nstreams} streams x 2.0 s of the cfg2-batch workload ({frames.value} frames), "
-                       f"oracle port (restated Spectrogram.cpp loop, radix-2 FFT stand-in, restated palette); "
+    fps, frames = run(nstreams, threads)
+    return dict(value=fps, unit="frames/s", cores=threads, kind=kind,
+                sample=f"{nstreams} streams x 2.0 s of the cfg2-batch workload ({frames} frames); {what}; "
                        f"1-thread rate {fps1:.0f} frames/s (calibration {cal:.1f} s)",
                 single_thread_value=fps1)
 
@@ -134,32 +154,25 @@ def run_reference(args):
     if rank != 0:
         return
     steps, warm = args.steps, args.warmup
-    import ctypes as C
-
-    import oracle_lib as O
-    import signals
     threads = os.cpu_count() or 1
-    cfg = O.BatchCfg(FS, N_FFT, HOP, O.WIN["hann"], CHANNELS, O.MIX["absmean"], O.PAL["jade"], 256, 0, -50.0, 50.0, 0)
-    x = signals.streams(1, CHANNELS, int(FS * 2.0), FS, kind="mix")[0]
-    frames = C.c_long(0)
-    lib = O.lib()
-    # one step = `threads` streams x 2 s (bounded sample of the workload); ~0.2-0.5 s per step
-    per_step_streams = threads
+    run, kind, what = _cpu_runner()
+    # one step = 4 streams per host thread x 2 s (bounded sample of the workload)
+    per_step_streams = 4 * threads
+    frames = 0
     for _ in range(warm):
-        lib.jo_bench_batch(C.byref(cfg), x.reshape(-1), x.shape[1], per_step_streams, threads, C.byref(frames))
+        run(per_step_streams, threads)
     t0 = time.time()
     total = 0
     for _ in range(steps):
-        lib.jo_bench_batch(C.byref(cfg), x.reshape(-1), x.shape[1], per_step_streams, threads, C.byref(frames))
-        total += frames.value
+        _, frames = run(per_step_streams, threads)
+        total += frames
     dt = time.time() - t0
     fps = total / dt
-    sample = (f"each step = {per_step_streams} streams x 2.0 s of cfg2-batch ({frames.value} frames) on {threads} host "
-              f"threads; CPU oracle port of Spectrogram.cpp:37-135 + CColorpalette lookup (FFT stand-in, parity unpinned)")
+    sample = (f"each step = {per_step_streams} streams x 2.0 s of cfg2-batch ({frames} frames) on {threads} host threads; {what}")
     line = dict(impl="reference", metric="stft_frames_per_sec", value=fps, unit="frames/s", n_gpus=args.gpus, steps=steps,
                 warmup=warm, ms_per_step=dt / steps * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype="f32", data="synthetic", config=dict(WORKLOAD, streams_per_step=per_step_streams, seconds_per_stream=2.0),
-                cpu_baseline=dict(value=fps, unit="frames/s", cores=threads, kind="port", sample=sample),
+                cpu_baseline=dict(value=fps, unit="frames/s", cores=threads, kind=kind, sample=sample),
                 e2e=dict(value=fps, unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line))
 

@@ -116,10 +116,58 @@ def ref():
         so = ORACLE_DIR / "_ref" / "libjade_ref.so"
         if not so.exists():
             return None
+        lib()  # libjade_ref.so resolves jo_power_f32 (the FFT stand-in) from liboracle.so
         L = C.CDLL(str(so))
         _bind_pal(L, "jr_pal_")
+        L.has_spec = hasattr(L, "jr_spec_create")
+        if L.has_spec:
+            _bind_ref_spec(L)
         _ref = L
     return _ref
+
+
+def _bind_ref_spec(L):
+    """The reference's real Spectrogram / SpectrogramComponent (oracle/ref_glue.cpp)."""
+    L.jr_spec_create.restype = C.c_void_p
+    for n, a in [("destroy", []), ("set_samplerate", [C.c_float]), ("set_channels", [C.c_size_t]),
+                 ("set_fftsize", [C.c_size_t]), ("set_closest_fftsize_ms", [C.c_float]),
+                 ("set_memory_time_s", [C.c_float]), ("set_feed_percent", [C.c_int]), ("set_pause", [C.c_int]),
+                 ("set_window", [C.c_int]), ("set_mix_mode", [C.c_int])]:
+        f = getattr(L, "jr_spec_" + n)
+        f.argtypes = [C.c_void_p] + a
+        f.restype = None
+    L.jr_spec_next_pow2.argtypes = [C.c_void_p, C.c_float]
+    L.jr_spec_next_pow2.restype = C.c_size_t
+    for n in ("spectrum_size", "memory_size", "feed_samples", "feed_blocks"):
+        f = getattr(L, "jr_spec_" + n)
+        f.argtypes = [C.c_void_p]
+        f.restype = C.c_int
+    L.jr_spec_samplerate.argtypes = [C.c_void_p]
+    L.jr_spec_samplerate.restype = C.c_float
+    L.jr_spec_window.argtypes = [C.c_void_p, f32p, C.c_int]
+    L.jr_spec_process_block.argtypes = [C.c_void_p, f32p]
+    L.jr_spec_get_mem.argtypes = [C.c_void_p, f32p, C.c_int, C.POINTER(C.c_int)]
+    L.jr_view_create.argtypes = [C.c_void_p]
+    L.jr_view_create.restype = C.c_void_p
+    L.jr_view_destroy.argtypes = [C.c_void_p]
+    L.jr_view_set_running.argtypes = [C.c_void_p, C.c_int]
+    L.jr_view_set_color_range.argtypes = [C.c_void_p, C.c_float, C.c_float]
+    L.jr_view_set_scheme.argtypes = [C.c_void_p, C.c_int]
+    L.jr_view_force_recompute.argtypes = [C.c_void_p]
+    L.jr_view_tick.argtypes = [C.c_void_p]
+    L.jr_view_tick.restype = None
+    L.jr_view_width.argtypes = [C.c_void_p]
+    L.jr_view_height.argtypes = [C.c_void_p]
+    L.jr_view_pixels.argtypes = [C.c_void_p]
+    L.jr_view_pixels.restype = C.POINTER(C.c_uint32)
+    L.jr_bench_batch.argtypes = [C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
+                                 f32p, C.c_long, C.c_int, C.c_int, C.POINTER(C.c_long)]
+    L.jr_bench_batch.restype = C.c_double
+
+
+def have_ref_spec():
+    r = ref()
+    return r is not None and r.has_spec
 
 
 class Palette:
@@ -177,28 +225,73 @@ class Palette:
 
 
 class Spec:
-    """Restated Spectrogram (oracle)."""
+    """Restated Spectrogram (oracle), or with use_ref=True the reference's REAL class compiled in oracle/_ref."""
 
-    def __init__(self):
-        self.L = lib()
-        self.h = self.L.jo_spec_create()
+    def __init__(self, use_ref=False):
+        self.L = ref() if use_ref else lib()
+        self.pre = "jr_spec_" if use_ref else "jo_spec_"
+        self.h = getattr(self.L, self.pre + "create")()
 
     def __getattr__(self, name):
-        f = getattr(self.L, "jo_spec_" + name)
+        f = getattr(self.L, self.pre + name)
         return lambda *a: f(self.h, *a)
 
     def process(self, planar):
         planar = np.ascontiguousarray(planar, np.float32)
-        return self.L.jo_spec_process_block(self.h, planar.reshape(-1))
+        return getattr(self.L, self.pre + "process_block")(self.h, planar.reshape(-1))
 
     def get_mem(self, mem):
         pos = C.c_int(0)
-        r = self.L.jo_spec_get_mem(self.h, mem.reshape(-1), mem.shape[0], C.byref(pos))
+        r = getattr(self.L, self.pre + "get_mem")(self.h, mem.reshape(-1), mem.shape[0], C.byref(pos))
         return r, pos.value
 
     def __del__(self):
         try:
-            self.L.jo_spec_destroy(self.h)
+            getattr(self.L, self.pre + "destroy")(self.h)
+        except Exception:
+            pass
+
+
+class View:
+    """SpectrogramComponent::timerCallback image assembly: restated (oracle) or the reference's real one."""
+
+    def __init__(self, spec, pal=None, use_ref=False):
+        self.use_ref = use_ref
+        self.spec = spec
+        self.pal = pal
+        if use_ref:
+            self.L = ref()
+            self.pre = "jr_view_"
+            self.h = self.L.jr_view_create(spec.h)
+        else:
+            self.L = lib()
+            self.pre = "jo_view_"
+            self.h = self.L.jo_view_create(spec.h, pal.h)
+
+    def _c(self, name, *a):
+        return getattr(self.L, self.pre + name)(self.h, *a)
+
+    def tick(self):
+        return self._c("tick")
+
+    def set_running(self, on):
+        self._c("set_running", int(on))
+
+    def set_color_range(self, mn, mx):
+        self._c("set_color_range", float(mn), float(mx))
+        if not self.use_ref:
+            self._c("force_recompute")
+
+    def force_recompute(self):
+        self._c("force_recompute")
+
+    def image(self):
+        h, w = self._c("height"), self._c("width")
+        return np.ctypeslib.as_array(self._c("pixels"), shape=(h, w)).copy()
+
+    def __del__(self):
+        try:
+            self._c("destroy")
         except Exception:
             pass
 

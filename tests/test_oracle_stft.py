@@ -4,6 +4,7 @@ product's host-side window / row-map tables (host-only entry points of libjade_g
 import ctypes as C
 import hashlib
 import pathlib
+import sys
 
 import numpy as np
 import pytest
@@ -263,3 +264,42 @@ def test_log_rows_cover_the_band_monotonically():
     assert hi[-1] == N // 2 + 1 or hi[-1] == N // 2
     wide = hi - lo > 1
     assert (lo[1:][wide[1:]] == hi[:-1][wide[1:]]).all()  # once bands are wider than a bin they tile without gaps
+
+
+# ---------------------------------------------------------------- goldens produced by the reference's REAL class
+GOLD_R = np.load(pathlib.Path(__file__).parent / "golden" / "spectrogram_ref.npz")
+
+
+def test_oracle_matches_reference_class_goldens():
+    """tests/golden/spectrogram_ref.npz holds outputs of the reference's own Spectrogram / timerCallback code compiled in
+    place (tools/gen_golden.py: reference_class); the restated oracle must reproduce them bit for bit."""
+    sys.path.insert(0, str(pathlib.Path(__file__).resolve().parent.parent / "tools"))
+    from gen_golden import REF_CASES, ref_case_inputs
+    for name in O.WIN:
+        for n in (64, 1024):
+            assert np.array_equal(O.window(name, n).view(np.uint32), GOLD_R[f"window_{name}_{n}"].view(np.uint32)), (name, n)
+    for name, N, feed, ch, win, nblocks in REF_CASES:
+        cfg = GOLD_R[name + "_cfg"]
+        s = O.Spec()
+        s.set_samplerate(48000.0)
+        s.set_memory_time_s(0.1)
+        s.set_channels(ch)
+        s.set_fftsize(N)
+        s.set_feed_percent(O.FEED[feed])
+        s.set_window(O.WIN[win])
+        W, B = s.memory_size(), s.spectrum_size()
+        assert (W, B) == (int(cfg[5]), int(cfg[6]))
+        pal = O.Palette(256, O.PAL["jade"])
+        view = O.View(s, pal)
+        view.tick()
+        x = ref_case_inputs(N, ch, nblocks)
+        for b in range(nblocks):
+            s.process(x[:, b * N:(b + 1) * N])
+        view.tick()
+        assert np.array_equal(view.image(), GOLD_R[name + "_image"]), name
+        for b in range(nblocks):
+            s.process(x[:, b * N:(b + 1) * N])
+        mem = np.zeros((W, B), np.float32)
+        newvals, pos = s.get_mem(mem)
+        assert (newvals, pos) == (int(cfg[7]), int(cfg[8])), name
+        assert np.array_equal(mem.view(np.uint32), GOLD_R[name + "_ring_db"].view(np.uint32)), name

@@ -7,6 +7,10 @@
   windows.npz      -- the six unit-RMS window tables at N = 64 and 2048 from the oracle restatement of setWindowFkt
                       (Spectrogram.cpp:239-293), and sha256 digests at N = 65536.
   pipeline.npz     -- seeded inputs with the oracle's dB columns and ARGB pixels for small end-to-end cases.
+  spectrogram_ref.npz -- outputs of the REFERENCE's own Spectrogram class and SpectrogramComponent::timerCallback
+                      (Spectrogram.cpp compiled in place against the stub JUCE/TGM headers of oracle/shim/, FFT = the
+                      oracle's float32 stand-in): window tables, dB rings after streaming seeded blocks through
+                      processSynchronBlock/getMem for every feed percentage, and the assembled image.
 
     python tools/gen_golden.py
 """
@@ -101,7 +105,54 @@ def pipeline():
     print("pipeline.npz", len(out), "arrays")
 
 
+REF_CASES = [("n256_p100_mono", 256, "p100", 1, "hann", 6), ("n512_p50_stereo", 512, "p50", 2, "blackmanharris", 5),
+             ("n1024_p25_stereo", 1024, "p25", 2, "hann", 4), ("n512_p10_mono", 512, "p10", 1, "hannpoisson", 4)]
+
+
+def ref_case_inputs(N, ch, nblocks):
+    return signals.streams(1, ch, N * nblocks, 48000.0, kind="mix", seed=100 + N + ch)[0]
+
+
+def reference_class():
+    assert O.have_ref_spec(), "oracle/_ref/libjade_ref.so lacks the Spectrogram glue: run `make -C oracle`"
+    out = {}
+    for name in O.WIN:  # the real setWindowFkt (Spectrogram.cpp:239-293)
+        for n in (64, 1024):
+            r = O.Spec(use_ref=True)
+            r.set_fftsize(n)
+            r.set_window(O.WIN[name])
+            w = np.empty(n, np.float32)
+            assert O.ref().jr_spec_window(r.h, w, n) == 0
+            out[f"window_{name}_{n}"] = w
+    for name, N, feed, ch, win, nblocks in REF_CASES:
+        r = O.Spec(use_ref=True)
+        r.set_samplerate(48000.0)
+        r.set_memory_time_s(0.1)
+        r.set_channels(ch)
+        r.set_fftsize(N)
+        r.set_feed_percent(O.FEED[feed])
+        r.set_window(O.WIN[win])
+        W, B = r.memory_size(), r.spectrum_size()
+        view = O.View(r, use_ref=True)
+        view.tick()
+        x = ref_case_inputs(N, ch, nblocks)
+        mem = np.zeros((W, B), np.float32)
+        for b in range(nblocks):
+            r.process(x[:, b * N:(b + 1) * N])
+        view.tick()
+        img = view.image()
+        for b in range(nblocks):  # second pass so that getMem below sees exactly these columns again
+            r.process(x[:, b * N:(b + 1) * N])
+        newvals, pos = r.get_mem(mem)
+        out[name + "_cfg"] = np.array([N, O.FEED[feed], ch, O.WIN[win], nblocks, W, B, newvals, pos], np.int32)
+        out[name + "_ring_db"] = mem
+        out[name + "_image"] = img
+    np.savez_compressed(OUT / "spectrogram_ref.npz", **out)
+    print("spectrogram_ref.npz", len(out), "arrays")
+
+
 if __name__ == "__main__":
     palettes()
     windows()
     pipeline()
+    reference_class()
