@@ -18,7 +18,9 @@
 
 #include "../../include/jade_gpu.h"
 #include "jade_host_tables.h"
+#define JADE_HELPER_KERNELS 1
 #include "jade_kernels.cuh"
+#include "jade_pk.cuh"
 
 using jade::KParams;
 
@@ -30,6 +32,7 @@ typedef void (*kernel_fn)(const KParams);
 
 struct KernelChoice {
     kernel_fn fn = nullptr;
+    kernel_fn fn_db = nullptr; // variant that also stores the float dB column (only where the two differ)
     int threads = 0;
     int smem = 0;
     int blocks_per_sm = 1;
@@ -38,23 +41,18 @@ struct KernelChoice {
     int family = 0; // 0 warp, 1 cta, 2 cta2
 };
 
-// (mix kind, general epilogue) -> kernel instantiation; Max/Min only exist with the general epilogue
-template <int T>
-kernel_fn pick_warp(int mixk, bool general)
-{
-    if (mixk == jade::MIX_SEL) return (kernel_fn)jade::stft_warp_kernel<T, jade::MIX_SEL, true>;
-    if (mixk == jade::MIX_SUM)
-        return general ? (kernel_fn)jade::stft_warp_kernel<T, jade::MIX_SUM, true> : (kernel_fn)jade::stft_warp_kernel<T, jade::MIX_SUM, false>;
-    return general ? (kernel_fn)jade::stft_warp_kernel<T, jade::MIX_NONE, true> : (kernel_fn)jade::stft_warp_kernel<T, jade::MIX_NONE, false>;
-}
-template <int R1>
-kernel_fn pick_cta(int mixk, bool general)
-{
-    if (mixk == jade::MIX_SEL) return (kernel_fn)jade::stft_cta_kernel<R1, jade::MIX_SEL, true>;
-    if (mixk == jade::MIX_SUM)
-        return general ? (kernel_fn)jade::stft_cta_kernel<R1, jade::MIX_SUM, true> : (kernel_fn)jade::stft_cta_kernel<R1, jade::MIX_SUM, false>;
-    return general ? (kernel_fn)jade::stft_cta_kernel<R1, jade::MIX_NONE, true> : (kernel_fn)jade::stft_cta_kernel<R1, jade::MIX_NONE, false>;
-}
+// Kernel instantiations live in their own translation units (jade_k_*.cu) so that they compile in parallel; each
+// unit hands out function pointers.  (mix kind, general epilogue) -> instantiation; Max/Min only exist with the general
+// epilogue.
+} // namespace
+namespace jade_k {
+typedef void (*kernel_fn)(const jade::KParams);
+kernel_fn warp_kernel(int T, int mixk, bool general);             // jade_k_warp_a.cu / jade_k_warp_b.cu
+kernel_fn cta_kernel(int R1, int mixk, bool general);             // jade_k_cta.cu
+kernel_fn cta2_kernel(int mixk);                                  // jade_k_cta.cu
+kernel_fn pk2048_kernel(int mixk, bool want_db, bool guard);      // jade_k_pk.cu
+} // namespace jade_k
+namespace {
 
 struct DevBuf {
     void* p = nullptr;
@@ -118,6 +116,7 @@ struct jade_engine {
     int N = 0, M = 0, B = 0, R = 0, W = 0;
     int k_lo = 0, k_hi = 0;
     KernelChoice kc;
+    KernelChoice kc_edge;  // family 3 only: guarded-load instantiation for boundary columns / unaligned geometries
     int mixk = 0;          // jade::MIX_NONE / MIX_SUM / MIX_SEL
     bool general = false;  // general (rolled) epilogue: pooled / cropped rows, precise dB, non-2^n channel mean, Max/Min
     bool pooled = false;
@@ -185,40 +184,62 @@ int choose_kernel(jade_engine* e)
     const int N = e->N;
     const int mu = e->mixk;
     const bool po = e->general;
-    if (N <= 2048) {
+    if (N == 2048 && !po && mu != jade::MIX_SEL) {
+        // headline path: packed-FP32x2 kernel (jade_pk.cuh)
+        kc.family = 3;
+        kc.threads = jade::PkCfg::WARPS * 32;
+        kc.units_per_block = jade::PkCfg::WARPS;
+        kc.smem = jade::PkCfg::smem_bytes(e->npal);
+        snprintf(kc.name, sizeof kc.name, "pk2048");
+        KernelChoice ke = kc; // boundary columns / unaligned geometries: same arithmetic, guarded loads
+        snprintf(ke.name, sizeof ke.name, "pk2048-guard");
+        kc.fn = jade_k::pk2048_kernel(mu, false, false);
+        kc.fn_db = jade_k::pk2048_kernel(mu, true, false);
+        ke.fn = jade_k::pk2048_kernel(mu, true, true);
+        ke.fn_db = nullptr;
+        CU(e, cudaFuncSetAttribute((const void*)kc.fn_db, cudaFuncAttributeMaxDynamicSharedMemorySize, kc.smem));
+        CU(e, cudaFuncSetAttribute((const void*)ke.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, ke.smem));
+        int occ_e = 0;
+        CU(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_e, (const void*)ke.fn, ke.threads, ke.smem));
+        if (occ_e < 1) return fail(e, JADE_ERR_CUDA, "kernel %s does not fit on an SM (smem %d)", ke.name, ke.smem);
+        ke.blocks_per_sm = occ_e;
+        e->kc_edge = ke;
+    } else if (N <= 2048) {
         const int T = N / 64;
         kc.family = 0;
         kc.threads = jade::WARP_KERNEL_WARPS * 32;
         kc.units_per_block = jade::WARP_KERNEL_WARPS * (32 / T);
         snprintf(kc.name, sizeof kc.name, "warp<%d>", T);
+        kc.fn = jade_k::warp_kernel(T, mu, po);
         switch (T) {
-        case 1: kc.fn = pick_warp<1>(mu, po); kc.smem = jade::WarpCfg<1>::smem_bytes(e->npal, po); break;
-        case 2: kc.fn = pick_warp<2>(mu, po); kc.smem = jade::WarpCfg<2>::smem_bytes(e->npal, po); break;
-        case 4: kc.fn = pick_warp<4>(mu, po); kc.smem = jade::WarpCfg<4>::smem_bytes(e->npal, po); break;
-        case 8: kc.fn = pick_warp<8>(mu, po); kc.smem = jade::WarpCfg<8>::smem_bytes(e->npal, po); break;
-        case 16: kc.fn = pick_warp<16>(mu, po); kc.smem = jade::WarpCfg<16>::smem_bytes(e->npal, po); break;
-        case 32: kc.fn = pick_warp<32>(mu, po); kc.smem = jade::WarpCfg<32>::smem_bytes(e->npal, po); break;
+        case 1: kc.smem = jade::WarpCfg<1>::smem_bytes(e->npal, po); break;
+        case 2: kc.smem = jade::WarpCfg<2>::smem_bytes(e->npal, po); break;
+        case 4: kc.smem = jade::WarpCfg<4>::smem_bytes(e->npal, po); break;
+        case 8: kc.smem = jade::WarpCfg<8>::smem_bytes(e->npal, po); break;
+        case 16: kc.smem = jade::WarpCfg<16>::smem_bytes(e->npal, po); break;
+        case 32: kc.smem = jade::WarpCfg<32>::smem_bytes(e->npal, po); break;
         default: return fail(e, JADE_ERR_ARG, "unsupported fft_size %d", N);
         }
+        if (!kc.fn) return fail(e, JADE_ERR_ARG, "unsupported fft_size %d", N);
     } else if (N <= 32768) {
         const int R1 = N / 2048;
         kc.family = 1;
         kc.threads = 32 * R1;
         snprintf(kc.name, sizeof kc.name, "cta<%d>", R1);
+        kc.fn = jade_k::cta_kernel(R1, mu, po);
         switch (R1) {
-        case 2: kc.fn = pick_cta<2>(mu, po); kc.smem = jade::CtaCfg<2>::smem_bytes(e->npal, po); break;
-        case 4: kc.fn = pick_cta<4>(mu, po); kc.smem = jade::CtaCfg<4>::smem_bytes(e->npal, po); break;
-        case 8: kc.fn = pick_cta<8>(mu, po); kc.smem = jade::CtaCfg<8>::smem_bytes(e->npal, po); break;
-        case 16: kc.fn = pick_cta<16>(mu, po); kc.smem = jade::CtaCfg<16>::smem_bytes(e->npal, po); break;
+        case 2: kc.smem = jade::CtaCfg<2>::smem_bytes(e->npal, po); break;
+        case 4: kc.smem = jade::CtaCfg<4>::smem_bytes(e->npal, po); break;
+        case 8: kc.smem = jade::CtaCfg<8>::smem_bytes(e->npal, po); break;
+        case 16: kc.smem = jade::CtaCfg<16>::smem_bytes(e->npal, po); break;
         default: return fail(e, JADE_ERR_ARG, "unsupported fft_size %d", N);
         }
+        if (!kc.fn) return fail(e, JADE_ERR_ARG, "unsupported fft_size %d", N);
     } else if (N == 65536) {
         kc.family = 2;
         kc.threads = 32 * 16;
         snprintf(kc.name, sizeof kc.name, "cta2<16>");
-        kc.fn = mu == jade::MIX_SEL ? (kernel_fn)jade::stft_cta2_kernel<16, jade::MIX_SEL>
-              : mu == jade::MIX_SUM ? (kernel_fn)jade::stft_cta2_kernel<16, jade::MIX_SUM>
-                                    : (kernel_fn)jade::stft_cta2_kernel<16, jade::MIX_NONE>;
+        kc.fn = jade_k::cta2_kernel(mu);
         kc.smem = jade::CtaCfg<16>::smem_bytes(e->npal, false);
     } else {
         return fail(e, JADE_ERR_ARG, "unsupported fft_size %d (power of two in [64,65536])", N);
@@ -296,27 +317,70 @@ void fill_params(jade_engine* e, KParams& P)
 }
 
 // grid size: persistent, a multiple of the SM count when there is enough work
-int grid_for(jade_engine* e, long long frames)
+int grid_for(jade_engine* e, const KernelChoice& kc, long long frames)
 {
-    const long long blocks_needed = (frames + e->kc.units_per_block - 1) / e->kc.units_per_block;
-    const long long cap = (long long)e->sm_count * e->kc.blocks_per_sm;
+    const long long blocks_needed = (frames + kc.units_per_block - 1) / kc.units_per_block;
+    const long long cap = (long long)e->sm_count * kc.blocks_per_sm;
     return (int)std::max<long long>(1, std::min(blocks_needed, cap));
 }
 
-int launch_stft(jade_engine* e, KParams& P, cudaStream_t st)
+int launch_one(jade_engine* e, const KernelChoice& kc, KParams& P, cudaStream_t st)
 {
     const long long frames = (long long)P.ncols * P.nstreams;
     if (frames <= 0) return 0;
-    const int grid = grid_for(e, frames);
-    if (e->kc.family == 2) {
+    const int grid = grid_for(e, kc, frames);
+    if (kc.family == 2) {
         const size_t need_e = (size_t)grid * (e->N / 4 + 1) * sizeof(jade::cpx);
         const size_t need_p = (size_t)grid * (e->N / 2 + 1) * sizeof(float);
         if (e->d_scratch_e.bytes < need_e || e->d_scratch_p.bytes < need_p)
             return fail(e, JADE_ERR_STATE, "scratch not sized for grid %d", grid);
     }
     void* args[] = {(void*)&P};
-    CU(e, cudaLaunchKernel((const void*)e->kc.fn, dim3(grid), dim3(e->kc.threads), args, e->kc.smem, st));
+    const kernel_fn fn = (P.db && kc.fn_db) ? kc.fn_db : kc.fn;
+    CU(e, cudaLaunchKernel((const void*)fn, dim3(grid), dim3(kc.threads), args, kc.smem, st));
     e->launches++;
+    return 0;
+}
+
+// columns [a, b) of the launch described by P (same output buffers)
+KParams sub_range(jade_engine* e, const KParams& P, long long a, long long b)
+{
+    KParams Q = P;
+    const long long off = a - P.first_col;
+    Q.first_col = a;
+    Q.ncols = (int)(b - a);
+    if (P.ring_w > 0) {
+        Q.ring_col0 = P.ring_col0 + off;
+    } else {
+        if (Q.pix) Q.pix += off * e->R;
+        if (Q.db) Q.db += off * e->B;
+    }
+    return Q;
+}
+
+int launch_stft(jade_engine* e, KParams& P, cudaStream_t st)
+{
+    if ((long long)P.ncols * P.nstreams <= 0) return 0;
+    if (e->kc.family != 3) return launch_one(e, e->kc, P, st);
+    // packed N = 2048 kernel: interior, 8-byte aligned frames; the rest goes to its guarded-load instantiation
+    if (!P.aligned2) return launch_one(e, e->kc_edge, P, st);
+    const long long j0 = P.first_col, j1 = P.first_col + P.ncols;
+    auto start = [&](long long j) { return frame_start_abs(e->cfg, j) - P.sample_base; };
+    long long lo = j0, hi = j1;
+    while (lo < j1 && start(lo) < 0) ++lo;                       // frame starts are monotone in j
+    while (hi > lo && start(hi - 1) + e->N > P.nsamples) --hi;
+    if (hi > lo) {
+        KParams Q = sub_range(e, P, lo, hi);
+        if (int r = launch_one(e, e->kc, Q, st)) return r;
+    }
+    if (lo > j0) {
+        KParams Q = sub_range(e, P, j0, lo);
+        if (int r = launch_one(e, e->kc_edge, Q, st)) return r;
+    }
+    if (j1 > hi) {
+        KParams Q = sub_range(e, P, hi, j1);
+        if (int r = launch_one(e, e->kc_edge, Q, st)) return r;
+    }
     return 0;
 }
 

@@ -1,0 +1,32 @@
+// jade_k_cta.cu -- instantiations of stft_cta_kernel<R1> and stft_cta2_kernel<16> (jade_kernels.cuh).
+#include "jade_kernels.cuh"
+namespace jade_k {
+typedef void (*kernel_fn)(const jade::KParams);
+namespace {
+template <int R1>
+kernel_fn pick(int mixk, bool general)
+{
+    using namespace jade;
+    if (mixk == MIX_SEL) return (kernel_fn)stft_cta_kernel<R1, MIX_SEL, true>;
+    if (mixk == MIX_SUM) return general ? (kernel_fn)stft_cta_kernel<R1, MIX_SUM, true> : (kernel_fn)stft_cta_kernel<R1, MIX_SUM, false>;
+    return general ? (kernel_fn)stft_cta_kernel<R1, MIX_NONE, true> : (kernel_fn)stft_cta_kernel<R1, MIX_NONE, false>;
+}
+} // namespace
+kernel_fn cta_kernel(int R1, int mixk, bool general)
+{
+    switch (R1) {
+    case 2: return pick<2>(mixk, general);
+    case 4: return pick<4>(mixk, general);
+    case 8: return pick<8>(mixk, general);
+    case 16: return pick<16>(mixk, general);
+    default: return nullptr;
+    }
+}
+kernel_fn cta2_kernel(int mixk)
+{
+    using namespace jade;
+    return mixk == MIX_SEL ? (kernel_fn)stft_cta2_kernel<16, MIX_SEL>
+         : mixk == MIX_SUM ? (kernel_fn)stft_cta2_kernel<16, MIX_SUM>
+                           : (kernel_fn)stft_cta2_kernel<16, MIX_NONE>;
+}
+} // namespace jade_k

@@ -32,6 +32,8 @@
 #define JADE_RESTRICT
 #define JADE_LOG2F(x) ::log2f(x)
 #define JADE_FDIV(a, b) ((a) / (b))
+#define JADE_FMUL(a, b) ((a) * (b))
+#define JADE_FADD(a, b) ((a) + (b))
 #else
 #define JADE_KERNEL(...) __global__ void __launch_bounds__(__VA_ARGS__)
 #define JADE_DYN_SMEM(name) extern __shared__ float4 name[]
@@ -45,6 +47,9 @@ __device__ __forceinline__ float jade_lg2(float x)
 }
 #define JADE_LOG2F(x) jade_lg2(x)
 #define JADE_FDIV(a, b) __fdiv_rn((a), (b))
+// explicitly rounded (never contracted into an FFMA): every kernel instantiation must produce the same bits
+#define JADE_FMUL(a, b) __fmul_rn((a), (b))
+#define JADE_FADD(a, b) __fadd_rn((a), (b))
 #endif
 
 namespace jade {
@@ -100,10 +105,10 @@ struct KParams {
 };
 
 // 10*log10(p + 1e-11) (Spectrogram.cpp:36,107).  Fast: one MUFU.LG2 + one FMUL (|err| ~ 1e-5 dB).
-JADE_DEVICE float to_db_fast(float p) { return 3.01029995663981195f * JADE_LOG2F(p + 1e-11f); }
+JADE_DEVICE float to_db_fast(float p) { return JADE_FMUL(3.01029995663981195f, JADE_LOG2F(JADE_FADD(p, 1e-11f))); }
 // Exactly the reference's arithmetic: float add, double log10, double multiply, float store.
 #if defined(__CUDACC__)
-__device__ __noinline__
+static __device__ __noinline__
 #else
 inline
 #endif
@@ -120,8 +125,8 @@ JADE_DEVICE uint32_t colour_of(float v, const KParams& P, const uint32_t* pal)
 {
     v = (v >= P.pmax) ? P.pmaxc : v;
     v = fmaxf(v, P.pmin);            // == `if (v < m_Min) v = m_Min` for every non-NaN v
-    const float d = v - P.pmin;
-    int idx = (int)(d * P.pmult);
+    const float d = JADE_FADD(v, -P.pmin);
+    int idx = (int)JADE_FMUL(d, P.pmult);
     idx = max(min(idx, P.npal - 1), 0);
     return pal[idx];
 }
@@ -402,7 +407,7 @@ JADE_KERNEL(WARP_KERNEL_WARPS * 32, (T >= 4 && !GENERAL) ? 2 : 1) stft_warp_kern
 #pragma unroll
             for (int q = 0; q < 33; ++q) {
                 if (q == 32 && s != 0) break;
-                const float d = to_db_fast(MIXK == MIX_SUM ? acc[q] * scale : acc[q]);
+                const float d = to_db_fast(MIXK == MIX_SUM ? JADE_FMUL(acc[q], scale) : acc[q]);
                 const uint32_t c = colour_of(d, P, s_pal);
                 if (drow) drow[T * q] = d;
                 if (prow) prow[-T * q] = c;
@@ -544,7 +549,7 @@ JADE_KERNEL(32 * R1, 1) stft_cta_kernel(const KParams P)
             for (int q = 0; q < 33; ++q) {
                 if (q == 32 && t != 0) break;
                 const int k = t + THREADS * q;
-                const float d = to_db_fast(MIXK == MIX_SUM ? acc[q] * scale : acc[q]);
+                const float d = to_db_fast(MIXK == MIX_SUM ? JADE_FMUL(acc[q], scale) : acc[q]);
                 const uint32_t c = colour_of(d, P, s_pal);
                 if (o.db) o.db[k] = d;
                 if (o.pix) o.pix[M - k] = c;
@@ -647,8 +652,9 @@ JADE_KERNEL(32 * R1, 1) stft_cta2_kernel(const KParams P)
 }
 
 // =========================================================================================================
-// Small helper kernels
+// Small helper kernels (non-template: compiled only into the translation unit that defines JADE_HELPER_KERNELS)
 // =========================================================================================================
+#if defined(JADE_HELPER_KERNELS) || defined(JADE_EMU)
 // Re-colour stored dB columns (ring or batch) -- SpectrogramComponent's m_recomputeAll path (Spectrogram.cpp:623-657)
 JADE_KERNEL(256) recolor_kernel(const KParams P, const float* dbcols, long long ncolumns)
 {
@@ -709,5 +715,6 @@ JADE_KERNEL(256) synth_kernel(float* out, long long stream_stride, long long cha
         out[st * stream_stride + ch * channel_stride + n] = v;
     }
 }
+#endif // JADE_HELPER_KERNELS
 
 } // namespace jade

@@ -4,6 +4,7 @@
 #include "cuda_emu.h"
 
 #include "../../jadespectrogram_b200/csrc/jade_kernels.cuh"
+#include "../../jadespectrogram_b200/csrc/jade_pk.cuh"
 #include "../../jadespectrogram_b200/csrc/jade_host_tables.h"
 #include "../../include/jade_gpu.h"
 
@@ -107,7 +108,43 @@ extern "C" int emu_render(const jade_config* cin, const int32_t* palette, int np
     P.db_stream_stride = (long long)ncols * B;
     std::vector<jade::cpx> se;
     std::vector<float> sp;
-    if (N <= 2048) {
+    if (N == 2048 && !general && multi != jade::MIX_SEL) {
+        // same routing as launch_stft in jade_gpu.cu: interior columns -> packed kernel, boundary columns -> warp<32>
+        jade_host::twiddle_matrix(1024, 32, 32, twI);
+        P.twI = reinterpret_cast<const jade::cpx*>(twI.data());
+        auto start = [&](long long j) {
+            return (j / c.frames_per_block) * (long long)c.block_stride + (j % c.frames_per_block) * (long long)c.hop - c.preroll;
+        };
+        const long long j0 = first_col, j1 = first_col + ncols;
+        long long lo = j0, hi = j1;
+        while (lo < j1 && start(lo) < 0) ++lo;
+        while (hi > lo && start(hi - 1) + N > nsamples) --hi;
+        if (!P.aligned2) lo = hi = j0; // everything through the guarded instantiation
+        auto sub = [&](long long a, long long b) {
+            KParams Q = P;
+            Q.first_col = a;
+            Q.ncols = (int)(b - a);
+            if (Q.pix) Q.pix += (a - j0) * R;
+            if (Q.db) Q.db += (a - j0) * B;
+            return Q;
+        };
+        const int smem = jade::PkCfg::smem_bytes(npal);
+        const int block = jade::PkCfg::WARPS * 32;
+        if (hi > lo) {
+            const KParams Q = sub(lo, hi);
+            if (multi == jade::MIX_SUM && db) jade_emu::launch(jade::stft_pk2048_kernel<jade::MIX_SUM, true, false>, grid, block, smem, Q);
+            else if (multi == jade::MIX_SUM) jade_emu::launch(jade::stft_pk2048_kernel<jade::MIX_SUM, false, false>, grid, block, smem, Q);
+            else if (db) jade_emu::launch(jade::stft_pk2048_kernel<jade::MIX_NONE, true, false>, grid, block, smem, Q);
+            else jade_emu::launch(jade::stft_pk2048_kernel<jade::MIX_NONE, false, false>, grid, block, smem, Q);
+        }
+        for (int edge = 0; edge < 2; ++edge) {
+            const long long a = edge ? hi : j0, b = edge ? j1 : lo;
+            if (b <= a) continue;
+            const KParams Q = sub(a, b);
+            if (multi == jade::MIX_SUM) jade_emu::launch(jade::stft_pk2048_kernel<jade::MIX_SUM, true, true>, grid, block, smem, Q);
+            else jade_emu::launch(jade::stft_pk2048_kernel<jade::MIX_NONE, true, true>, grid, block, smem, Q);
+        }
+    } else if (N <= 2048) {
         const int T = N / 64;
         jade_host::twiddle_matrix(32 * T, 32, T, twI);
         P.twI = reinterpret_cast<const jade::cpx*>(twI.data());
