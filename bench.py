@@ -193,6 +193,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # NCCL prints its version banner on stdout when NCCL_DEBUG is set; stdout carries exactly one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     steps, warm = args.steps, max(args.warmup, 3)
@@ -323,6 +325,8 @@ def run_ours(args):
                         parallelism=f"streams sharded over {world} GPU(s), no collective", kernel=eng.kernel_name),
             e2e=e2e, gpu_launches=int(launches), clocks=clocks, latency=lat,
             roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic,
+                          traffic_unit="DRAM bytes per launch (ncu dram__bytes_read+write, profiles/traffic.json)",
+                          algorithmic_bytes_per_launch=BYTES_ALG * frames_step,
                           peak_source=peak_src, bytes_per_frame=BYTES_ALG, frames_per_launch=frames_step,
                           kernel_ms=kernel_ms),
             cpu_baseline=cpu)
@@ -345,7 +349,14 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--only-kernel", action="store_true", help="device-resident loop only (for ncu)")
+    ap.add_argument("--geometry", default=None, help="experiments only: FFT,HOP,CHANNELS instead of the cfg2-batch workload")
     args = ap.parse_args()
+    if args.geometry:
+        global N_FFT, HOP, CHANNELS, ROWS, BYTES_ALG, WORKLOAD
+        N_FFT, HOP, CHANNELS = (int(v) for v in args.geometry.split(","))
+        ROWS = N_FFT // 2 + 1
+        BYTES_ALG = 4 * HOP * CHANNELS + 4 * ROWS
+        WORKLOAD = dict(WORKLOAD, workload=f"custom-{N_FFT}-{HOP}-{CHANNELS}", fft_size=N_FFT, hop=HOP, channels=CHANNELS, rows=ROWS)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -4,10 +4,11 @@ The library is the product; this module only declares its symbols.  It fails lou
 missing or has no usable GPU -- there is no CPU path.
 """
 import ctypes as C
+import os
 import pathlib
 
 PKG_DIR = pathlib.Path(__file__).resolve().parent
-LIB_PATH = PKG_DIR / "libjade_gpu.so"
+LIB_PATH = pathlib.Path(os.environ.get("JADE_GPU_LIB", PKG_DIR / "libjade_gpu.so"))  # override: kernel-variant experiments
 
 # enums (include/jade_gpu.h)
 MIX = dict(absmean=0, max=1, min=2, left=3, right=4)
