@@ -21,6 +21,7 @@
 #define JADE_HELPER_KERNELS 1
 #include "jade_kernels.cuh"
 #include "jade_pk.cuh"
+#include "jade_pk_cta.cuh"
 
 using jade::KParams;
 
@@ -49,7 +50,8 @@ namespace jade_k {
 typedef void (*kernel_fn)(const jade::KParams);
 kernel_fn warp_kernel(int T, int mixk, bool general);             // jade_k_warp_a.cu / jade_k_warp_b.cu
 kernel_fn cta_kernel(int R1, int mixk, bool general);             // jade_k_cta.cu
-kernel_fn cta2_kernel(int mixk);                                  // jade_k_cta.cu
+kernel_fn pkcta_kernel(int R1, int mixk, bool want_db);           // jade_k_pkcta.cu
+kernel_fn pkcta2_kernel(int mixk);                                // jade_k_pkcta.cu
 kernel_fn pk2048_kernel(int mixk, bool want_db, bool guard);      // jade_k_pk.cu
 } // namespace jade_k
 namespace {
@@ -226,21 +228,29 @@ int choose_kernel(jade_engine* e)
         kc.family = 1;
         kc.threads = 32 * R1;
         snprintf(kc.name, sizeof kc.name, "cta<%d>", R1);
-        kc.fn = jade_k::cta_kernel(R1, mu, po);
+        const bool packed = !po && mu != jade::MIX_SEL; // fast path: packed FP32x2 kernels (jade_pk_cta.cuh)
+        if (packed) {
+            snprintf(kc.name, sizeof kc.name, "pkcta<%d>", R1);
+            kc.fn = jade_k::pkcta_kernel(R1, mu, false);
+            kc.fn_db = jade_k::pkcta_kernel(R1, mu, true);
+        } else {
+            kc.fn = jade_k::cta_kernel(R1, mu, po);
+        }
         switch (R1) {
-        case 2: kc.smem = jade::CtaCfg<2>::smem_bytes(e->npal, po); break;
-        case 4: kc.smem = jade::CtaCfg<4>::smem_bytes(e->npal, po); break;
-        case 8: kc.smem = jade::CtaCfg<8>::smem_bytes(e->npal, po); break;
-        case 16: kc.smem = jade::CtaCfg<16>::smem_bytes(e->npal, po); break;
+        case 2: kc.smem = packed ? jade::PkCtaCfg<2>::smem_bytes(e->npal, false) : jade::CtaCfg<2>::smem_bytes(e->npal, po); break;
+        case 4: kc.smem = packed ? jade::PkCtaCfg<4>::smem_bytes(e->npal, false) : jade::CtaCfg<4>::smem_bytes(e->npal, po); break;
+        case 8: kc.smem = packed ? jade::PkCtaCfg<8>::smem_bytes(e->npal, false) : jade::CtaCfg<8>::smem_bytes(e->npal, po); break;
+        case 16: kc.smem = packed ? jade::PkCtaCfg<16>::smem_bytes(e->npal, false) : jade::CtaCfg<16>::smem_bytes(e->npal, po); break;
         default: return fail(e, JADE_ERR_ARG, "unsupported fft_size %d", N);
         }
         if (!kc.fn) return fail(e, JADE_ERR_ARG, "unsupported fft_size %d", N);
+        if (kc.fn_db) CU(e, cudaFuncSetAttribute((const void*)kc.fn_db, cudaFuncAttributeMaxDynamicSharedMemorySize, kc.smem));
     } else if (N == 65536) {
         kc.family = 2;
         kc.threads = 32 * 16;
-        snprintf(kc.name, sizeof kc.name, "cta2<16>");
-        kc.fn = jade_k::cta2_kernel(mu);
-        kc.smem = jade::CtaCfg<16>::smem_bytes(e->npal, false);
+        snprintf(kc.name, sizeof kc.name, "pkcta2<16>");
+        kc.fn = jade_k::pkcta2_kernel(mu);
+        kc.smem = jade::PkCtaCfg<16>::smem_bytes(e->npal, false);
     } else {
         return fail(e, JADE_ERR_ARG, "unsupported fft_size %d (power of two in [64,65536])", N);
     }

@@ -1,4 +1,4 @@
-// jade_k_cta.cu -- instantiations of stft_cta_kernel<R1> and stft_cta2_kernel<16> (jade_kernels.cuh).
+// jade_k_cta.cu -- instantiations of stft_cta_kernel<R1> (jade_kernels.cuh; general-epilogue path of N >= 4096).
 #include "jade_kernels.cuh"
 namespace jade_k {
 typedef void (*kernel_fn)(const jade::KParams);
@@ -21,12 +21,5 @@ kernel_fn cta_kernel(int R1, int mixk, bool general)
     case 16: return pick<16>(mixk, general);
     default: return nullptr;
     }
-}
-kernel_fn cta2_kernel(int mixk)
-{
-    using namespace jade;
-    return mixk == MIX_SEL ? (kernel_fn)stft_cta2_kernel<16, MIX_SEL>
-         : mixk == MIX_SUM ? (kernel_fn)stft_cta2_kernel<16, MIX_SUM>
-                           : (kernel_fn)stft_cta2_kernel<16, MIX_NONE>;
 }
 } // namespace jade_k

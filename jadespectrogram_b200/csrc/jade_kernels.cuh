@@ -14,7 +14,8 @@
 //                                              two radix passes (32 x T) with one shared-memory transpose per warp.
 //   stft_cta_kernel<R1>   N = 2048*R1 <= 32768: CTA of R1 warps; radix-R1 column pass, then one 1024-point row FFT
 //                                              per warp (same register code), rows staged in shared memory.
-//   (N = 65536 is built from two half-size real FFTs, see stft_cta2_kernel.)
+//   The fast paths of N >= 2048 live in jade_pk.cuh / jade_pk_cta.cuh (packed FP32x2 arithmetic); N = 65536 is built
+//   from two half-size real FFTs there (stft_pkcta2_kernel).
 //
 // The real-input FFT packs z[m] = x[2m] + i x[2m+1] (M = N/2 complex points) and finishes with the split
 //   X[k] = (Z[k] + conj Z[M-k]) - i W_N^k (Z[k] - conj Z[M-k])      (window table is pre-multiplied by 1/2)
@@ -564,90 +565,6 @@ JADE_KERNEL(32 * R1, 1) stft_cta_kernel(const KParams P)
             emit_general_rows(P, s_pal, o, spec, t, THREADS);
             __syncthreads();
         }
-    }
-}
-
-// =========================================================================================================
-// Class C: N = 4096*R1 (R1 = 16 -> N = 65536) from two half-size real FFTs (decimation in time on the REAL data):
-//   X[k] = E[k] + W_N^k O[k],  X[N/2-k] = conj(E[k] - W_N^k O[k]),  k = 0..N/4
-// E / O = real FFT (size N/2, M2 = N/4 = 1024*R1 complex points) of the even / odd windowed samples.
-// The complex working set of one half (8*M2 bytes) fits in shared memory; E and the mixed power spectrum go
-// through an L2-resident per-CTA scratch slot; the epilogue is the general one.
-// =========================================================================================================
-template <int R1, int MIXK>
-JADE_KERNEL(32 * R1, 1) stft_cta2_kernel(const KParams P)
-{
-    using Cfg = CtaCfg<R1>;
-    constexpr int M2 = Cfg::M;      // complex points per half
-    constexpr int NH = 2 * M2;      // real points per half  (= N/2)
-    constexpr int N = 2 * NH;
-    constexpr int THREADS = Cfg::THREADS;
-    JADE_DYN_SMEM(smem);
-    char* sm = reinterpret_cast<char*>(smem);
-    cpx* rowbuf = reinterpret_cast<cpx*>(sm + Cfg::off_row);
-    cpx* s_twI = reinterpret_cast<cpx*>(sm + Cfg::off_twI);
-    uint32_t* s_pal = reinterpret_cast<uint32_t*>(sm + Cfg::off_pal);
-
-    const int t = threadIdx.x;
-    for (int i = t; i < 1024; i += THREADS) s_twI[i] = P.twI[i];
-    for (int i = t; i < P.npal; i += THREADS) s_pal[i] = P.palette[i];
-    __syncthreads();
-
-    cpx* se = P.scratch_e + (long long)blockIdx.x * (M2 + 1);
-    float* sp = P.scratch_p + (long long)blockIdx.x * (NH + 1);
-    const unsigned total = (unsigned)P.ncols * (unsigned)P.nstreams;
-    int ch0, ch1;
-    channel_range(P, ch0, ch1);
-
-    for (unsigned g = blockIdx.x; g < total; g += gridDim.x) {
-        const int stream = (int)(g / (unsigned)P.ncols);
-        const long long j = P.first_col + (g - (unsigned)stream * (unsigned)P.ncols);
-        const long long st = frame_start(P, j);
-        const bool fast = st >= 0 && st + N <= P.nsamples;
-
-        for (int ch = ch0; ch < (MIXK == MIX_NONE ? ch0 + 1 : ch1); ++ch) {
-            const float* x = P.samples + stream * P.stream_stride + ch * P.channel_stride;
-            const long long ns = P.nsamples;
-            const float* JADE_RESTRICT win = P.window;
-            for (int half = 0; half < 2; ++half) {
-                // z[m] = xw[4m + half] + i xw[4m + 2 + half]
-                cta_fft<R1>(rowbuf, s_twI, P.twA, [&](int m) {
-                    const long long i0 = st + 4LL * m + half, i1 = i0 + 2;
-                    const float a = (fast || (i0 >= 0 && i0 < ns)) ? x[i0] : 0.f;
-                    const float b = (fast || (i1 >= 0 && i1 < ns)) ? x[i1] : 0.f;
-                    return mk(a * win[4 * m + half], b * win[4 * m + 2 + half]);
-                });
-                for (int k = t; k <= M2; k += THREADS) {
-                    const cpx zk = rowbuf_get<R1>(rowbuf, k & (M2 - 1));
-                    const cpx zp = rowbuf_get<R1>(rowbuf, (M2 - k) & (M2 - 1));
-                    const cpx hv = split_value(zk, zp, P.twH[k]); // E[k] or O[k]
-                    if (half == 0) {
-                        se[k] = hv;
-                    } else {
-                        const cpx e = se[k];
-                        const cpx q = cmul(hv, P.twP[k]);
-                        const float ar = e.x + q.x, ai = e.y + q.y, br = e.x - q.x, bi = e.y - q.y;
-                        const float p1 = fm(ar, ar, ai * ai), p2 = fm(br, br, bi * bi);
-                        const int k2 = NH - k;
-                        float a1 = mix_init<MIXK>(P.mix_mode), a2 = a1;
-                        if (MIXK != MIX_NONE && ch != ch0) {
-                            a1 = sp[k];
-                            a2 = sp[k2];
-                        }
-                        mix_add<MIXK>(a1, p1, P.mix_mode);
-                        mix_add<MIXK>(a2, p2, P.mix_mode);
-                        sp[k] = a1;
-                        if (k2 != k) sp[k2] = a2;
-                    }
-                }
-                __syncthreads();
-            }
-        }
-        const ColOut o = col_out(P, stream, j);
-        emit_general_bins(P, s_pal, o, sp, t, THREADS);
-        __syncthreads();
-        emit_general_rows(P, s_pal, o, sp, t, THREADS);
-        __syncthreads();
     }
 }
 

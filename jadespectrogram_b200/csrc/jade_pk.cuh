@@ -132,35 +132,46 @@ JADE_DEVICE void pk_inner(f2* a)
         pk_inner<LEN, BASE, J + 1>(a);
     }
 }
-template <int LEN, int BASE>
+template <int R, int LEN, int BASE>
 JADE_DEVICE void pk_blocks(f2* a)
 {
-    if constexpr (BASE < 32) {
+    if constexpr (BASE < R) {
         pk_inner<LEN, BASE, 0>(a);
-        pk_blocks<LEN, BASE + LEN>(a);
+        pk_blocks<R, LEN, BASE + LEN>(a);
     }
 }
-template <int LEN>
+template <int R, int LEN>
 JADE_DEVICE void pk_stages(f2* a)
 {
-    if constexpr (LEN <= 32) {
-        pk_blocks<LEN, 0>(a);
-        pk_stages<LEN * 2>(a);
+    if constexpr (LEN <= R) {
+        pk_blocks<R, LEN, 0>(a);
+        pk_stages<R, LEN * 2>(a);
     }
 }
-// in-place 32-point DFT, bit-reversed input, natural-order output (same convention as fft_dit<32>)
-JADE_DEVICE void fft32_pk(f2* a) { pk_stages<2>(a); }
+// in-place R-point DFT (R = 2..32), bit-reversed input, natural-order output (same convention as fft_dit<R>)
+template <int R>
+JADE_DEVICE void fft_pk(f2* a)
+{
+    pk_stages<R, 2>(a);
+}
 // the same after its first (twiddle-free) stage has been applied by the caller
-JADE_DEVICE void fft32_pk_after_stage1(f2* a) { pk_stages<4>(a); }
+template <int R>
+JADE_DEVICE void fft_pk_after_stage1(f2* a)
+{
+    pk_stages<R, 4>(a);
+}
+JADE_DEVICE void fft32_pk(f2* a) { fft_pk<32>(a); }
+JADE_DEVICE void fft32_pk_after_stage1(f2* a) { fft_pk_after_stage1<32>(a); }
 
-// Window multiply fused with the first radix-2 stage of the pass-1 DFT.  Stage 1 pairs n1 = j and j + 16 and leaves
-// them in v[2 brev4(j)], v[2 brev4(j) + 1]:   v0 = x_j w_j + x_{j+16} w_{j+16},  v1 = x_j w_j - x_{j+16} w_{j+16}
+// Window multiply fused with the first radix-2 stage of the pass-1 DFT.  Stage 1 of an R-point DFT pairs n1 = j and
+// j + R/2 and leaves them in v[2 brev(j)], v[2 brev(j) + 1]:   v0 = x_j w_j + x_{j+R/2} w_{j+R/2},  v1 = x_j w_j - x_{j+R/2} w_{j+R/2}
 // written as ONE product and two FFMA2 (3 instructions instead of 4).  The fusion is spelled out because ptxas
 // contracts mul.f32x2 + add.f32x2 pairs on its own where it can, which would make differently-compiled instantiations
 // of the kernel round differently; with the explicit form every instantiation (and the CPU emulator) agrees bit for bit.
+template <int R = 32>
 JADE_DEVICE void win_stage1(f2* v, int j, f2 xa, f2 wa, f2 xb, f2 wb)
 {
-    const int i = brev(j, 4);
+    const int i = brev(j, ilog2c(R) - 1);
     const f2 va = mul2(xa, wa);
     v[2 * i] = fma2(xb, wb, va);
     v[2 * i + 1] = fma2(neg2(xb), wb, va);

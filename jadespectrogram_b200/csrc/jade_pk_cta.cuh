@@ -1,0 +1,294 @@
+// jade_pk_cta.cuh -- large transforms (N = 4096 ... 65536) with the packed FP32x2 arithmetic of jade_pk.cuh.
+//
+// One CTA of R1 warps transforms one frame of M = 1024 R1 complex points z[m] = x[2m] + i x[2m+1] that live in shared
+// memory (BASELINE configs[2]: N = 16384 -> 64 KB; "large-FFT smem staging"):
+//   column pass : thread owns columns n2 (32/R1 of them), loads z[n2 + 1024 n1] straight from global memory with the
+//                 window multiply fused into the first radix-2 stage, radix-R1 DFT in registers, twiddle W_M^(n2 k1),
+//                 row k1 of the shared-memory matrix;
+//   row pass    : warp k1 transforms its 1024-point row with the register code of the N = 2048 kernel (radix-32,
+//                 twiddle, in-place XOR-swizzled transpose, radix-32) and leaves it in natural order;
+//   split       : thread handles the pairs (k, M-k), k = t + 32 R1 q: A = Z[k] + conj Z[M-k], B = Z[k] - conj Z[M-k],
+//                 T = (-i W_N^k) B, X[k] = A + T, X[M-k] = conj(A - T); powers accumulate over channels in registers;
+//   epilogue    : dB (MUFU.LG2), CColorPalette lookup, one packed pixel per row, rows M-k and k, coalesced.
+// N = 65536 (configs[4]) does not fit (256 KB): it is built from two half-size real FFTs (even / odd samples) combined
+// by one radix-2 step, with E and the mixed power spectrum in an L2-resident per-CTA scratch slot (general epilogue:
+// log-frequency max-pool rows).
+// Reference lines replaced: Spectrogram.cpp:50-56,137-145 (framing, window, spectrum::power), :64-107 (mix, dB),
+// :634-647 + CColorpalette.h:32-47 (pixel loops).
+#pragma once
+#include "jade_pk.cuh"
+
+namespace jade {
+
+template <int R1>
+struct PkCtaCfg {
+    static constexpr int M = 1024 * R1;
+    static constexpr int N = 2 * M;
+    static constexpr int B = M + 1;
+    static constexpr int THREADS = 32 * R1;
+    static constexpr int RS = 1024 + 16 / R1; // row stride (complex words): conflict-free split reads (see rowget)
+    static constexpr int TROW = 34;           // per-lane row of the 1024-point inter-pass twiddle table (32 + 16 B pad)
+    static constexpr int MINB = R1 >= 16 ? 1 : 16 / R1; // CTAs per SM aimed at (16 warps of 128 registers)
+    static constexpr int off_row = 0;
+    static constexpr int off_twI = off_row + R1 * RS * 8;
+    static constexpr int off_pal = off_twI + 32 * TROW * 8;
+    static JADE_HD int off_spec(int npal) { return off_pal + (npal * 4 + 15) / 16 * 16; }
+    static JADE_HD int smem_bytes(int npal, bool general) { return off_spec(npal) + (general ? ((B + 3) / 4) * 16 : 0); }
+};
+
+// Z[k] of the M-point transform inside the row matrix: k1 = k % R1 is the row, k / R1 the row-FFT bin
+template <int R1>
+JADE_DEVICE f2 rowget(const f2* rowbuf, int k)
+{
+    return rowbuf[(k & (R1 - 1)) * PkCtaCfg<R1>::RS + (k / R1)];
+}
+
+// M = 1024 R1 point complex FFT by the whole CTA.  ld(m, x, w) yields the raw sample pair and the window pair of
+// complex point m (the product is formed here, fused with stage 1).  Result in rowbuf (see rowget).
+template <int R1, typename Loader>
+JADE_DEVICE void cta_fft_pk(f2* rowbuf, const f2* s_twI, const cpx* JADE_RESTRICT twA, Loader ld)
+{
+    using Cfg = PkCtaCfg<R1>;
+    constexpr int RS = Cfg::RS, CPT = 32 / R1, H = R1 / 2;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) {
+        const int n2 = t + Cfg::THREADS * c;
+        f2 a[R1];
+#pragma unroll
+        for (int j = 0; j < H; ++j) { // stage 1 pairs n1 = j and j + R1/2
+            f2 xa, wa, xb, wb;
+            ld(n2 + 1024 * j, xa, wa);
+            ld(n2 + 1024 * (j + H), xb, wb);
+            win_stage1<R1>(a, j, xa, wa, xb, wb);
+        }
+        fft_pk_after_stage1<R1>(a);
+#pragma unroll
+        for (int k1 = 0; k1 < R1; ++k1) {
+            if (k1 == 0) {
+                rowbuf[n2] = a[0];
+            } else {
+                const cpx w = twA[k1 * 1024 + n2];
+                rowbuf[k1 * RS + n2] = cmul2(a[k1], pk(w.x, w.y));
+            }
+        }
+    }
+    __syncthreads();
+    // row pass: warp `warp` transforms row k1 = warp (1024 points) in place
+    f2* row = rowbuf + warp * RS;
+    f2 v[32], u[32];
+#pragma unroll
+    for (int n1 = 0; n1 < 32; ++n1) v[brev(n1, 5)] = row[lane + 32 * n1];
+    __syncwarp();
+    fft32_pk(v);
+    const f2x2* trow = reinterpret_cast<const f2x2*>(s_twI + lane * Cfg::TROW);
+#pragma unroll
+    for (int k1 = 0; k1 < 32; k1 += 2) {
+        const f2x2 tw = trow[k1 / 2];
+        row[k1 * 32 + (lane ^ k1)] = (k1 == 0) ? v[0] : cmul2(v[k1], tw.a);
+        row[(k1 + 1) * 32 + (lane ^ (k1 + 1))] = cmul2(v[k1 + 1], tw.b);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int jx = 0; jx < 32; ++jx) u[brev(jx, 5)] = row[lane * 32 + (jx ^ lane)];
+    fft32_pk(u);
+    __syncwarp();
+#pragma unroll
+    for (int k2 = 0; k2 < 32; ++k2) row[lane + 32 * k2] = u[k2];
+    __syncthreads();
+}
+
+// per-lane [lane][k1] copy of the 1024-point inter-pass twiddles W_1024^(k1 lane) (P.twI is [k1][lane])
+template <int R1>
+JADE_DEVICE void stage_row_twiddles(f2* s_twI, const cpx* JADE_RESTRICT twI)
+{
+    for (int i = threadIdx.x; i < 1024; i += PkCtaCfg<R1>::THREADS) {
+        const int s = i & 31, k1 = i >> 5;
+        const cpx t = twI[k1 * 32 + s];
+        s_twI[s * PkCtaCfg<R1>::TROW + k1] = pk(t.x, t.y);
+    }
+}
+
+// N = 2048 R1 (R1 = 2, 4, 8, 16).  Identity rows in the reference orientation, hardware log2 dB.  Loads are always
+// bounds-checked per frame (one warp-uniform test selects the unchecked loop), the arithmetic is identical either way.
+template <int R1, int MIXK, bool WANT_DB>
+JADE_KERNEL(32 * R1, PkCtaCfg<R1>::MINB) stft_pkcta_kernel(const KParams P)
+{
+    using Cfg = PkCtaCfg<R1>;
+    constexpr int M = Cfg::M, N = Cfg::N, THREADS = Cfg::THREADS;
+    JADE_DYN_SMEM(smem);
+    char* sm = reinterpret_cast<char*>(smem);
+    f2* rowbuf = reinterpret_cast<f2*>(sm + Cfg::off_row);
+    f2* s_twI = reinterpret_cast<f2*>(sm + Cfg::off_twI);
+    uint32_t* s_pal = reinterpret_cast<uint32_t*>(sm + Cfg::off_pal);
+
+    const int t = threadIdx.x;
+    stage_row_twiddles<R1>(s_twI, P.twI);
+    for (int i = t; i < P.npal; i += THREADS) s_pal[i] = P.palette[i];
+    __syncthreads();
+
+    const unsigned total = (unsigned)P.ncols * (unsigned)P.nstreams;
+    int ch0, ch1;
+    channel_range(P, ch0, ch1);
+    const f2* JADE_RESTRICT winp = reinterpret_cast<const f2*>(P.window);
+    const float scale = (MIXK == MIX_SUM) ? (1.0f / (float)P.channels) : 1.0f;
+
+    for (unsigned g = blockIdx.x; g < total; g += gridDim.x) {
+        const int stream = (int)(g / (unsigned)P.ncols);
+        const long long j = P.first_col + (g - (unsigned)stream * (unsigned)P.ncols);
+        const long long st = frame_start(P, j);
+        const bool fast = P.aligned2 && st >= 0 && st + N <= P.nsamples;
+
+        float alo[16], ahi[16], amid = 0.f; // bins t + THREADS q / M - (t + THREADS q) / M/2 (thread 0)
+#pragma unroll
+        for (int q = 0; q < 16; ++q) alo[q] = ahi[q] = 0.f;
+
+        for (int ch = ch0; ch < (MIXK == MIX_NONE ? ch0 + 1 : ch1); ++ch) {
+            const float* x = P.samples + stream * P.stream_stride + ch * P.channel_stride;
+            const long long ns = P.nsamples;
+            if (fast) {
+                const f2* xz = reinterpret_cast<const f2*>(x + st);
+                cta_fft_pk<R1>(rowbuf, s_twI, P.twA, [&](int m, f2& xv, f2& wv) {
+                    xv = xz[m];
+                    wv = winp[m];
+                });
+            } else {
+                cta_fft_pk<R1>(rowbuf, s_twI, P.twA, [&](int m, f2& xv, f2& wv) {
+                    const cpx z = load_pair_guarded(x, st + 2 * m, ns);
+                    xv = pk(z.x, z.y);
+                    wv = winp[m];
+                });
+            }
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const int k = t + THREADS * q;
+                const f2 zk = rowget<R1>(rowbuf, k);
+                const f2 zp = rowget<R1>(rowbuf, (M - k) & (M - 1));
+                const cpx w = P.twP[k]; // W_N^k ; -i W_N^k = (w.y, -w.x)
+                const f2 A = add2(zk, conj2(zp));
+                const f2 Bv = sub2(zk, conj2(zp));
+                const f2 T = cmul2(Bv, pk(w.y, -w.x));
+                const f2 xp = add2(A, T), xm = sub2(A, T);
+                alo[q] = fm(lo(xp), lo(xp), fm(hi(xp), hi(xp), alo[q]));
+                ahi[q] = fm(lo(xm), lo(xm), fm(hi(xm), hi(xm), ahi[q]));
+            }
+            { // bin M/2 (self-paired): X = 2 conj Z
+                const f2 zm = rowget<R1>(rowbuf, M / 2);
+                const float a = lo(zm), b = hi(zm);
+                amid = fm(JADE_FMUL(4.0f, a), a, fm(JADE_FMUL(4.0f, b), b, amid));
+            }
+            __syncthreads();
+        }
+
+        const ColOut o = col_out(P, stream, j);
+        uint32_t* p_lo = o.pix ? o.pix + (M - t) : nullptr; // bin k -> row M - k
+        uint32_t* p_hi = o.pix ? o.pix + t : nullptr;       // bin M - k -> row k
+        float* d_lo = (WANT_DB && o.db) ? o.db + t : nullptr;
+        float* d_hi = (WANT_DB && o.db) ? o.db + (M - t) : nullptr;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const float dl = to_db_fast(MIXK == MIX_SUM ? JADE_FMUL(alo[q], scale) : alo[q]);
+            const float dh = to_db_fast(MIXK == MIX_SUM ? JADE_FMUL(ahi[q], scale) : ahi[q]);
+            if (WANT_DB && d_lo) {
+                d_lo[THREADS * q] = dl;
+                d_hi[-THREADS * q] = dh;
+            }
+            if (p_lo) {
+                p_lo[-THREADS * q] = colour_of(dl, P, s_pal);
+                p_hi[THREADS * q] = colour_of(dh, P, s_pal);
+            }
+        }
+        if (t == 0) {
+            const float dm = to_db_fast(MIXK == MIX_SUM ? JADE_FMUL(amid, scale) : amid);
+            if (WANT_DB && o.db) o.db[M / 2] = dm;
+            if (o.pix) o.pix[M / 2] = colour_of(dm, P, s_pal);
+        }
+    }
+}
+
+// N = 4096 R1 (R1 = 16 -> N = 65536) from two half-size real FFTs (decimation in time on the REAL data):
+//   X[k] = E[k] + W_N^k O[k],  X[N/2-k] = conj(E[k] - W_N^k O[k]),  k = 0..N/4
+// E / O = real FFT (size N/2, M2 = N/4 = 1024 R1 complex points) of the even / odd windowed samples.
+template <int R1, int MIXK>
+JADE_KERNEL(32 * R1, 1) stft_pkcta2_kernel(const KParams P)
+{
+    using Cfg = PkCtaCfg<R1>;
+    constexpr int M2 = Cfg::M;      // complex points per half
+    constexpr int NH = 2 * M2;      // real points per half  (= N/2)
+    constexpr int N = 2 * NH;
+    constexpr int THREADS = Cfg::THREADS;
+    JADE_DYN_SMEM(smem);
+    char* sm = reinterpret_cast<char*>(smem);
+    f2* rowbuf = reinterpret_cast<f2*>(sm + Cfg::off_row);
+    f2* s_twI = reinterpret_cast<f2*>(sm + Cfg::off_twI);
+    uint32_t* s_pal = reinterpret_cast<uint32_t*>(sm + Cfg::off_pal);
+
+    const int t = threadIdx.x;
+    stage_row_twiddles<R1>(s_twI, P.twI);
+    for (int i = t; i < P.npal; i += THREADS) s_pal[i] = P.palette[i];
+    __syncthreads();
+
+    f2* se = reinterpret_cast<f2*>(P.scratch_e) + (long long)blockIdx.x * (M2 + 1);
+    float* sp = P.scratch_p + (long long)blockIdx.x * (NH + 1);
+    const unsigned total = (unsigned)P.ncols * (unsigned)P.nstreams;
+    int ch0, ch1;
+    channel_range(P, ch0, ch1);
+
+    for (unsigned g = blockIdx.x; g < total; g += gridDim.x) {
+        const int stream = (int)(g / (unsigned)P.ncols);
+        const long long j = P.first_col + (g - (unsigned)stream * (unsigned)P.ncols);
+        const long long st = frame_start(P, j);
+        const bool fast = st >= 0 && st + N <= P.nsamples;
+
+        for (int ch = ch0; ch < (MIXK == MIX_NONE ? ch0 + 1 : ch1); ++ch) {
+            const float* x = P.samples + stream * P.stream_stride + ch * P.channel_stride;
+            const long long ns = P.nsamples;
+            const float* JADE_RESTRICT win = P.window;
+            for (int half = 0; half < 2; ++half) {
+                // z[m] = xw[4m + half] + i xw[4m + 2 + half]
+                cta_fft_pk<R1>(rowbuf, s_twI, P.twA, [&](int m, f2& xv, f2& wv) {
+                    const long long i0 = st + 4LL * m + half, i1 = i0 + 2;
+                    const float a = (fast || (i0 >= 0 && i0 < ns)) ? x[i0] : 0.f;
+                    const float b = (fast || (i1 >= 0 && i1 < ns)) ? x[i1] : 0.f;
+                    xv = pk(a, b);
+                    wv = pk(win[4 * m + half], win[4 * m + 2 + half]);
+                });
+                for (int k = t; k <= M2; k += THREADS) {
+                    const f2 zk = rowget<R1>(rowbuf, k & (M2 - 1));
+                    const f2 zp = rowget<R1>(rowbuf, (M2 - k) & (M2 - 1));
+                    const cpx wh = P.twH[k];
+                    // E[k] or O[k] = (Z[k] + conj Z[M2-k]) - i W (Z[k] - conj Z[M2-k])
+                    const f2 hv = add2(add2(zk, conj2(zp)), cmul2(sub2(zk, conj2(zp)), pk(wh.y, -wh.x)));
+                    if (half == 0) {
+                        se[k] = hv;
+                    } else {
+                        const f2 e = se[k];
+                        const cpx wp = P.twP[k];
+                        const f2 qv = cmul2(hv, pk(wp.x, wp.y));
+                        const f2 xa = add2(e, qv), xb = sub2(e, qv);
+                        const float p1 = fm(lo(xa), lo(xa), JADE_FMUL(hi(xa), hi(xa)));
+                        const float p2 = fm(lo(xb), lo(xb), JADE_FMUL(hi(xb), hi(xb)));
+                        const int k2 = NH - k;
+                        float a1 = mix_init<MIXK>(P.mix_mode), a2 = a1;
+                        if (MIXK != MIX_NONE && ch != ch0) {
+                            a1 = sp[k];
+                            a2 = sp[k2];
+                        }
+                        mix_add<MIXK>(a1, p1, P.mix_mode);
+                        mix_add<MIXK>(a2, p2, P.mix_mode);
+                        sp[k] = a1;
+                        if (k2 != k) sp[k2] = a2;
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        const ColOut o = col_out(P, stream, j);
+        emit_general_bins(P, s_pal, o, sp, t, THREADS);
+        __syncthreads();
+        emit_general_rows(P, s_pal, o, sp, t, THREADS);
+        __syncthreads();
+    }
+}
+
+} // namespace jade

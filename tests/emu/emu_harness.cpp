@@ -5,6 +5,7 @@
 
 #include "../../jadespectrogram_b200/csrc/jade_kernels.cuh"
 #include "../../jadespectrogram_b200/csrc/jade_pk.cuh"
+#include "../../jadespectrogram_b200/csrc/jade_pk_cta.cuh"
 #include "../../jadespectrogram_b200/csrc/jade_host_tables.h"
 #include "../../include/jade_gpu.h"
 
@@ -37,6 +38,16 @@ void run_cta(const KParams& P, int mixk, bool general, int grid)
     else if (mixk == jade::MIX_SUM) jade_emu::launch(jade::stft_cta_kernel<R1, jade::MIX_SUM, false>, grid, block, smem, P);
     else if (general) jade_emu::launch(jade::stft_cta_kernel<R1, jade::MIX_NONE, true>, grid, block, smem, P);
     else jade_emu::launch(jade::stft_cta_kernel<R1, jade::MIX_NONE, false>, grid, block, smem, P);
+}
+template <int R1>
+void run_pkcta(const KParams& P, int mixk, bool want_db, int npal, int grid)
+{
+    const int smem = jade::PkCtaCfg<R1>::smem_bytes(npal, false);
+    const int block = 32 * R1;
+    if (mixk == jade::MIX_SUM && want_db) jade_emu::launch(jade::stft_pkcta_kernel<R1, jade::MIX_SUM, true>, grid, block, smem, P);
+    else if (mixk == jade::MIX_SUM) jade_emu::launch(jade::stft_pkcta_kernel<R1, jade::MIX_SUM, false>, grid, block, smem, P);
+    else if (want_db) jade_emu::launch(jade::stft_pkcta_kernel<R1, jade::MIX_NONE, true>, grid, block, smem, P);
+    else jade_emu::launch(jade::stft_pkcta_kernel<R1, jade::MIX_NONE, false>, grid, block, smem, P);
 }
 } // namespace
 
@@ -171,10 +182,18 @@ extern "C" int emu_render(const jade_config* cin, const int32_t* palette, int np
             sp.resize((size_t)grid * (N / 2 + 1));
             P.scratch_e = se.data();
             P.scratch_p = sp.data();
-            const int smem = jade::CtaCfg<16>::smem_bytes(npal, false);
-            if (multi == jade::MIX_SEL) jade_emu::launch(jade::stft_cta2_kernel<16, jade::MIX_SEL>, grid, 512, smem, P);
-            else if (multi == jade::MIX_SUM) jade_emu::launch(jade::stft_cta2_kernel<16, jade::MIX_SUM>, grid, 512, smem, P);
-            else jade_emu::launch(jade::stft_cta2_kernel<16, jade::MIX_NONE>, grid, 512, smem, P);
+            const int smem = jade::PkCtaCfg<16>::smem_bytes(npal, false);
+            if (multi == jade::MIX_SEL) jade_emu::launch(jade::stft_pkcta2_kernel<16, jade::MIX_SEL>, grid, 512, smem, P);
+            else if (multi == jade::MIX_SUM) jade_emu::launch(jade::stft_pkcta2_kernel<16, jade::MIX_SUM>, grid, 512, smem, P);
+            else jade_emu::launch(jade::stft_pkcta2_kernel<16, jade::MIX_NONE>, grid, 512, smem, P);
+        } else if (!general && multi != jade::MIX_SEL) {
+            switch (R1) {
+            case 2: run_pkcta<2>(P, multi, db != nullptr, npal, grid); break;
+            case 4: run_pkcta<4>(P, multi, db != nullptr, npal, grid); break;
+            case 8: run_pkcta<8>(P, multi, db != nullptr, npal, grid); break;
+            case 16: run_pkcta<16>(P, multi, db != nullptr, npal, grid); break;
+            default: return -1;
+            }
         } else {
             switch (R1) {
             case 2: run_cta<2>(P, multi, general, grid); break;
