@@ -250,7 +250,7 @@ int choose_kernel(jade_engine* e)
         kc.threads = 32 * 16;
         snprintf(kc.name, sizeof kc.name, "pkcta2<16>");
         kc.fn = jade_k::pkcta2_kernel(mu);
-        kc.smem = jade::PkCtaCfg<16>::smem_bytes(e->npal, false);
+        kc.smem = jade::PkCtaCfg<16>::smem_bytes2(e->npal, e->pooled ? e->R : 0);
     } else {
         return fail(e, JADE_ERR_ARG, "unsupported fft_size %d (power of two in [64,65536])", N);
     }

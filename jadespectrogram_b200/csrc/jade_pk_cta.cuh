@@ -34,6 +34,8 @@ struct PkCtaCfg {
     static constexpr int off_pal = off_twI + 32 * TROW * 8;
     static JADE_HD int off_spec(int npal) { return off_pal + (npal * 4 + 15) / 16 * 16; }
     static JADE_HD int smem_bytes(int npal, bool general) { return off_spec(npal) + (general ? ((B + 3) / 4) * 16 : 0); }
+    // two-half kernel (N = 4096 R1): + the pooled-row table
+    static JADE_HD int smem_bytes2(int npal, int pooled_rows) { return off_spec(npal) + (pooled_rows * 8 + 15) / 16 * 16; }
 };
 
 // Z[k] of the M-point transform inside the row matrix: k1 = k % R1 is the row, k / R1 the row-FFT bin
@@ -223,9 +225,13 @@ JADE_KERNEL(32 * R1, 1) stft_pkcta2_kernel(const KParams P)
     f2* s_twI = reinterpret_cast<f2*>(sm + Cfg::off_twI);
     uint32_t* s_pal = reinterpret_cast<uint32_t*>(sm + Cfg::off_pal);
 
+    i2* s_rows = reinterpret_cast<i2*>(sm + Cfg::off_spec(P.npal)); // pooled rows: [R] bin ranges (smem_bytes2)
+
     const int t = threadIdx.x;
     stage_row_twiddles<R1>(s_twI, P.twI);
     for (int i = t; i < P.npal; i += THREADS) s_pal[i] = P.palette[i];
+    if (P.pooled)
+        for (int i = t; i < P.R; i += THREADS) s_rows[i] = P.row_bins[i];
     __syncthreads();
 
     f2* se = reinterpret_cast<f2*>(P.scratch_e) + (long long)blockIdx.x * (M2 + 1);
@@ -245,15 +251,42 @@ JADE_KERNEL(32 * R1, 1) stft_pkcta2_kernel(const KParams P)
             const long long ns = P.nsamples;
             const float* JADE_RESTRICT win = P.window;
             for (int half = 0; half < 2; ++half) {
-                // z[m] = xw[4m + half] + i xw[4m + 2 + half]
-                cta_fft_pk<R1>(rowbuf, s_twI, P.twA, [&](int m, f2& xv, f2& wv) {
-                    const long long i0 = st + 4LL * m + half, i1 = i0 + 2;
-                    const float a = (fast || (i0 >= 0 && i0 < ns)) ? x[i0] : 0.f;
-                    const float b = (fast || (i1 >= 0 && i1 < ns)) ? x[i1] : 0.f;
-                    xv = pk(a, b);
-                    wv = pk(win[4 * m + half], win[4 * m + 2 + half]);
-                });
-                for (int k = t; k <= M2; k += THREADS) {
+                // z[m] = xw[4m + half] + i xw[4m + 2 + half].  Three loaders, identical arithmetic afterwards:
+                // 16-byte vector loads (interior frame, 16-byte aligned), scalar loads (interior), branch-free guarded.
+                const float* xs = x + st;
+                if (fast && ((reinterpret_cast<uintptr_t>(xs) | reinterpret_cast<uintptr_t>(win)) & 15) == 0) {
+                    const float4* x4 = reinterpret_cast<const float4*>(xs);
+                    const float4* w4 = reinterpret_cast<const float4*>(win);
+                    if (half == 0) {
+                        cta_fft_pk<R1>(rowbuf, s_twI, P.twA, [&](int m, f2& xv, f2& wv) {
+                            const float4 a = x4[m], w = w4[m];
+                            xv = pk(a.x, a.z);
+                            wv = pk(w.x, w.z);
+                        });
+                    } else {
+                        cta_fft_pk<R1>(rowbuf, s_twI, P.twA, [&](int m, f2& xv, f2& wv) {
+                            const float4 a = x4[m], w = w4[m];
+                            xv = pk(a.y, a.w);
+                            wv = pk(w.y, w.w);
+                        });
+                    }
+                } else if (fast) {
+                    cta_fft_pk<R1>(rowbuf, s_twI, P.twA, [&](int m, f2& xv, f2& wv) {
+                        xv = pk(xs[4 * m + half], xs[4 * m + 2 + half]);
+                        wv = pk(win[4 * m + half], win[4 * m + 2 + half]);
+                    });
+                } else {
+                    cta_fft_pk<R1>(rowbuf, s_twI, P.twA, [&](int m, f2& xv, f2& wv) {
+                        const long long i0 = st + 4LL * m + half, i1 = i0 + 2;
+                        const long long c0 = i0 < 0 ? 0 : (i0 < ns ? i0 : ns - 1), c1 = i1 < 0 ? 0 : (i1 < ns ? i1 : ns - 1);
+                        const float a = x[c0], b = x[c1]; // clamped address, value selected afterwards: no branches
+                        xv = pk((i0 >= 0 && i0 < ns) ? a : 0.f, (i1 >= 0 && i1 < ns) ? b : 0.f);
+                        wv = pk(win[4 * m + half], win[4 * m + 2 + half]);
+                    });
+                }
+                // 32 independent iterations per thread (+ k = M2 on thread 0), unrolled so that the L2 round trips of
+                // several iterations are in flight together (one CTA of 16 warps per SM cannot hide them otherwise)
+                auto split_one = [&](int k) {
                     const f2 zk = rowget<R1>(rowbuf, k & (M2 - 1));
                     const f2 zp = rowget<R1>(rowbuf, (M2 - k) & (M2 - 1));
                     const cpx wh = P.twH[k];
@@ -279,15 +312,54 @@ JADE_KERNEL(32 * R1, 1) stft_pkcta2_kernel(const KParams P)
                         sp[k] = a1;
                         if (k2 != k) sp[k2] = a2;
                     }
-                }
+                };
+#pragma unroll 4
+                for (int q = 0; q < M2 / THREADS; ++q) split_one(t + THREADS * q);
+                if (t == 0) split_one(M2);
                 __syncthreads();
             }
         }
         const ColOut o = col_out(P, stream, j);
-        emit_general_bins(P, s_pal, o, sp, t, THREADS);
-        __syncthreads();
-        emit_general_rows(P, s_pal, o, sp, t, THREADS);
-        __syncthreads();
+        if (P.pooled && !o.db) {
+            // Log-frequency max-pool rows (configs[4]): the mixed power spectrum moves from the L2 scratch slot into the
+            // (now idle) shared-memory row matrix and is pooled there -- a scan of the L2 copy serialises ~250 dependent
+            // L2 round trips per row.
+            float* spec_s = reinterpret_cast<float*>(rowbuf); // B floats <= R1 * RS * 8 bytes
+            const bool mean = P.mix_mode == K_MIX_ABSMEAN && P.channels > 1;
+            const float nchf = (float)P.channels;
+#pragma unroll 8
+            for (int q = 0; q < NH / THREADS; ++q) {
+                const int k = t + THREADS * q;
+                const float p = sp[k];
+                spec_s[k] = mean ? JADE_FDIV(p, nchf) : p;
+            }
+            if (t == 0) spec_s[NH] = mean ? JADE_FDIV(sp[NH], nchf) : sp[NH];
+            __syncthreads();
+            // one thread per row, scanning its band in shared memory with four independent max chains; consecutive
+            // threads own consecutive rows, so the pixel stores coalesce.  (A warp-per-row scan with a shuffle max
+            // spends ~45 instructions per row on loop control for the many one-bin rows: measured 70 k warp
+            // instructions per frame against ~8 k for this form.)
+            for (int r = t; r < P.R; r += THREADS) {
+                const i2 rb = s_rows[r];
+                float m0 = spec_s[rb.lo], m1 = m0, m2 = m0, m3 = m0; // bands are never empty (jade_host::log_rows)
+                int k = rb.lo + 1;
+                for (; k + 3 < rb.hi; k += 4) {
+                    m0 = fmaxf(m0, spec_s[k]);
+                    m1 = fmaxf(m1, spec_s[k + 1]);
+                    m2 = fmaxf(m2, spec_s[k + 2]);
+                    m3 = fmaxf(m3, spec_s[k + 3]);
+                }
+                for (; k < rb.hi; ++k) m0 = fmaxf(m0, spec_s[k]);
+                const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+                if (o.pix) o.pix[P.flip ? (P.R - 1 - r) : r] = colour_of(to_db(mx, P.db_precise), P, s_pal);
+            }
+            __syncthreads();
+        } else {
+            emit_general_bins(P, s_pal, o, sp, t, THREADS);
+            __syncthreads();
+            emit_general_rows(P, s_pal, o, sp, t, THREADS);
+            __syncthreads();
+        }
     }
 }
 

@@ -22,6 +22,7 @@ struct BlockState {
     pthread_barrier_t block_bar;
     std::vector<pthread_barrier_t> warp_bar;
     std::vector<char> smem;
+    std::vector<float> mail; // one slot per thread: warp shuffles
 };
 inline thread_local dim3 t_threadIdx, t_blockIdx;
 inline dim3 g_blockDim, g_gridDim;
@@ -36,6 +37,16 @@ inline void* dyn_smem() { return g_block->smem.data(); }
 
 inline void __syncthreads() { pthread_barrier_wait(&jade_emu::g_block->block_bar); }
 inline void __syncwarp(unsigned = 0xffffffffu) { pthread_barrier_wait(&jade_emu::g_block->warp_bar[threadIdx.x >> 5]); }
+inline float __shfl_xor_sync(unsigned, float v, int lane_mask)
+{
+    jade_emu::BlockState& st = *jade_emu::g_block;
+    const unsigned tid = threadIdx.x;
+    st.mail[tid] = v;
+    __syncwarp();
+    const float r = st.mail[(tid & ~31u) | ((tid ^ (unsigned)lane_mask) & 31u)];
+    __syncwarp();
+    return r;
+}
 inline int max(int a, int b) { return a > b ? a : b; }
 inline int min(int a, int b) { return a < b ? a : b; }
 inline float sinpif(float x) { return (float)std::sin(M_PI * (double)x); }
@@ -50,6 +61,7 @@ void launch(K kernel, unsigned grid, unsigned block, size_t smem_bytes, A... arg
     for (unsigned b = 0; b < grid; ++b) {
         BlockState st;
         st.smem.assign(smem_bytes + 64, 0);
+        st.mail.assign(block, 0.f);
         pthread_barrier_init(&st.block_bar, nullptr, block);
         const unsigned nw = (block + 31) / 32;
         st.warp_bar.resize(nw);

@@ -182,7 +182,7 @@ extern "C" int emu_render(const jade_config* cin, const int32_t* palette, int np
             sp.resize((size_t)grid * (N / 2 + 1));
             P.scratch_e = se.data();
             P.scratch_p = sp.data();
-            const int smem = jade::PkCtaCfg<16>::smem_bytes(npal, false);
+            const int smem = jade::PkCtaCfg<16>::smem_bytes2(npal, pooled ? R : 0);
             if (multi == jade::MIX_SEL) jade_emu::launch(jade::stft_pkcta2_kernel<16, jade::MIX_SEL>, grid, 512, smem, P);
             else if (multi == jade::MIX_SUM) jade_emu::launch(jade::stft_pkcta2_kernel<16, jade::MIX_SUM>, grid, 512, smem, P);
             else jade_emu::launch(jade::stft_pkcta2_kernel<16, jade::MIX_NONE>, grid, 512, smem, P);

@@ -35,7 +35,7 @@ def lib():
     return _lib
 
 
-def render(cfg, palette, min_db, max_db, samples, first_col, ncols, rows, grid=2):
+def render(cfg, palette, min_db, max_db, samples, first_col, ncols, rows, grid=2, want_db=True):
     """samples [nstreams][channels][nsamples] float32 -> (db [nstreams][ncols][B], pix [nstreams][ncols][rows])."""
     samples = np.ascontiguousarray(samples, np.float32)
     nstreams, ch, ns = samples.shape
@@ -45,6 +45,6 @@ def render(cfg, palette, min_db, max_db, samples, first_col, ncols, rows, grid=2
     pix = np.zeros((nstreams, ncols, rows), np.uint32)
     db = np.zeros((nstreams, ncols, B), np.float32)
     r = lib().emu_render(C.byref(cfg), palette.ctypes.data, palette.size, min_db, max_db, samples.ctypes.data, nstreams, ns,
-                         first_col, ncols, grid, pix.ctypes.data, db.ctypes.data)
+                         first_col, ncols, grid, pix.ctypes.data, db.ctypes.data if want_db else None)
     assert r == rows, (r, rows)
     return db, pix

@@ -74,3 +74,22 @@ def test_emulated_general_epilogue_options():
     pooled = np.stack([odb[:, blo[r]:bhi[r]].max(axis=1) for r in range(R)], axis=1)
     parity.check_pixels(pix[0], (ref.lookup(pooled).astype(np.uint32) | np.uint32(0xFF000000))[:, ::-1], pooled[:, ::-1],
                         -80.0, 0.0, 64)
+
+
+def test_emulated_n65536_log_rows_without_db():
+    """BASELINE config 5 path: pixels only, log max-pool rows -> the warp-per-row pooled epilogue (shuffle max)."""
+    from jadespectrogram_b200 import _capi
+    N, hop, R, fs = 65536, 1024, 96, 192000.0
+    x = signals.streams(1, 1, N + hop * 3, fs)
+    pal = O.Palette(256, O.PAL["jade"]).table()
+    c = _cfg(N, hop, 1, "hann", "absmean", row_map=ROWS["log_maxpool"], rows=R, fmin=20.0, fmax=96000.0)
+    c.sample_rate = fs
+    _, pix = E.render(c, pal, -50.0, 50.0, x, 64, 3, R, grid=1, want_db=False)
+    odb, _ = O.render_batch(x[0], fs=fs, fft_size=N, hop=hop, first_col=64, ncols=3)
+    blo, bhi = np.zeros(R, np.int32), np.zeros(R, np.int32)
+    _capi.load().jade_log_rows(fs, N, R, 20.0, 96000.0, blo.ctypes.data, bhi.ctypes.data)
+    pooled = np.stack([odb[:, blo[r]:bhi[r]].max(axis=1) for r in range(R)], axis=1)
+    ref = O.Palette(256, O.PAL["jade"])
+    ref.set_value_range(-50.0, 50.0)
+    parity.check_pixels(pix[0], (ref.lookup(pooled).astype(np.uint32) | np.uint32(0xFF000000))[:, ::-1], pooled[:, ::-1],
+                        -50.0, 50.0, 256)
