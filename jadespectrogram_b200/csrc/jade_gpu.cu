@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -1052,7 +1053,13 @@ int jade_render_batch(jade_engine* e, const float* samples, int nstreams, int64_
     const bool db_pinned = db && pinned(db);
 
     // chunk shape
-    const size_t budget = (size_t)96 << 20; // bytes of output per chunk
+    // bytes of output per chunk: small enough that the pipeline's fill and drain (one chunk of H2D without a
+    // concurrent D2H and vice versa) stay a small share of a call, large enough to keep DMA and launch overheads negligible
+    static const size_t budget = []() {
+        const char* v = getenv("JADE_CHUNK_MB"); // tuning knob
+        const long mb = v ? atol(v) : 0;
+        return (size_t)(mb > 0 ? mb : 32) << 20;
+    }();
     const size_t col_bytes = (size_t)(pixels ? R * 4 : 0) + (size_t)(db ? B * 4 : 0);
     long long cols_per_chunk = ncols, streams_per_chunk = 1;
     if ((size_t)ncols * col_bytes > budget) {
