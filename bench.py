@@ -183,7 +183,7 @@ def run_ours(args):
     import torch.distributed as dist
 
     import signals
-    from jadespectrogram_b200 import Engine, host_alloc, host_free
+    from jadespectrogram_b200 import Engine, host_alloc, host_free, sharding
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -247,10 +247,7 @@ def run_ours(args):
         step()
     torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    max_ms = float(t.item())
+    max_ms = sharding.reduce_max(total_ms, dev)  # the slowest rank defines the job time
     value = frames_step * steps * world / (max_ms * 1e-3)
     kernel_ms = statistics.mean(per_launch_ms)
 
@@ -275,10 +272,7 @@ def run_ours(args):
     for _ in range(e2e_steps):
         eng.render_batch(h_in, out_pix=h_pix)
     e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = Se * ncols * e2e_steps * world / float(te.item())
+    e2e_value = Se * ncols * e2e_steps * world / sharding.reduce_max(e2e_s, dev)
     check = int(h_pix[0, ncols // 2].astype(np.uint64).sum())  # the step's result is read on the host
     e2e = dict(value=e2e_value, unit="frames/s", h2d_bytes_per_step=int(h_in.nbytes), d2h_bytes_per_step=int(h_pix.nbytes),
                steps=e2e_steps, streams_per_step=Se, api="jade_render_batch (pinned host buffers)", checksum=check)
