@@ -188,13 +188,19 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE JSON line: libraries that print there (NCCL's version banner) go to stderr instead
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(json_fd, (json.dumps(obj) + "\n").encode())
+
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # NCCL prints its version banner on stdout when NCCL_DEBUG is set; stdout carries exactly one JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     steps, warm = args.steps, max(args.warmup, 3)
@@ -253,8 +259,8 @@ def run_ours(args):
 
     if args.only_kernel:  # short command for ncu captures: no e2e / latency / CPU legs
         if rank == 0:
-            print(json.dumps(dict(metric="stft_frames_per_sec", value=value, unit="frames/s", n_gpus=world, steps=steps,
-                                  kernel_ms=kernel_ms, gpu_launches=int(launches), note="--only-kernel")))
+            emit(dict(metric="stft_frames_per_sec", value=value, unit="frames/s", n_gpus=world, steps=steps,
+                      kernel_ms=kernel_ms, gpu_launches=int(launches), note="--only-kernel"))
         eng.close()
         return
 
@@ -324,7 +330,7 @@ def run_ours(args):
                           peak_source=peak_src, bytes_per_frame=BYTES_ALG, frames_per_launch=frames_step,
                           kernel_ms=kernel_ms),
             cpu_baseline=cpu)
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
