@@ -7,9 +7,10 @@ template <int R1>
 kernel_fn pick(int mixk, bool general)
 {
     using namespace jade;
+    // the fast path of these sizes is stft_pkcta_kernel (jade_k_pkcta.cu); only the general epilogue lives here
+    if (!general && mixk != MIX_SEL) return nullptr;
     if (mixk == MIX_SEL) return (kernel_fn)stft_cta_kernel<R1, MIX_SEL, true>;
-    if (mixk == MIX_SUM) return general ? (kernel_fn)stft_cta_kernel<R1, MIX_SUM, true> : (kernel_fn)stft_cta_kernel<R1, MIX_SUM, false>;
-    return general ? (kernel_fn)stft_cta_kernel<R1, MIX_NONE, true> : (kernel_fn)stft_cta_kernel<R1, MIX_NONE, false>;
+    return mixk == MIX_SUM ? (kernel_fn)stft_cta_kernel<R1, MIX_SUM, true> : (kernel_fn)stft_cta_kernel<R1, MIX_NONE, true>;
 }
 } // namespace
 kernel_fn cta_kernel(int R1, int mixk, bool general)

@@ -17,7 +17,11 @@ kernel_fn warp_kernel(int T, int mixk, bool general)
 {
     switch (T) {
     case 16: return pick<16>(mixk, general);
-    case 32: return pick<32>(mixk, general);
+    case 32: // N = 2048: the fast path is stft_pk2048_kernel (jade_k_pk.cu); only the general epilogue lives here
+        if (!general && mixk != jade::MIX_SEL) return nullptr;
+        return mixk == jade::MIX_SEL ? (kernel_fn)jade::stft_warp_kernel<32, jade::MIX_SEL, true>
+             : mixk == jade::MIX_SUM ? (kernel_fn)jade::stft_warp_kernel<32, jade::MIX_SUM, true>
+                                     : (kernel_fn)jade::stft_warp_kernel<32, jade::MIX_NONE, true>;
     default: return warp_kernel_small(T, mixk, general);
     }
 }

@@ -8,7 +8,8 @@ frames = float(sys.argv[4]) if len(sys.argv) > 4 else 1.0
 raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr = rows[1]; col = {h: i for i, h in enumerate(hdr)}
-counts = [(r[col["Source"]].strip(), int(r[col["Instructions Executed"]] or 0), int(r[col["# Samples"]] or 0)) for r in rows[2:] if len(r) >= len(hdr)]
+counts = [(r[col["Source"]].strip(), int(r[col["Instructions Executed"]] or 0), int(r[col["# Samples"]] or 0),
+           int(r[col["L1 Wavefronts Shared"]] or 0), int(r[col["L1 Wavefronts Shared Excessive"]] or 0)) for r in rows[2:] if len(r) >= len(hdr)]
 d = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(obj)], cwd=d, check=True, stdout=subprocess.DEVNULL)
 cubin = [f for f in os.listdir(d) if f.endswith(".cubin")][0]
@@ -24,10 +25,11 @@ for ln in sec.splitlines():
     if re.match(r"\s+/\*[0-9a-f]{4,5}\*/\s+\S", ln):
         order.append(line)
 assert len(order) == len(counts), (len(order), len(counts))
-by = collections.Counter(); st = collections.Counter()
-for (f_l, (src, n, s)) in zip(order, counts):
-    by[f_l] += n; st[f_l] += s
+by = collections.Counter(); st = collections.Counter(); wf = collections.Counter(); wx = collections.Counter()
+for (f_l, (src, n, s, w, x)) in zip(order, counts):
+    by[f_l] += n; st[f_l] += s; wf[f_l] += w; wx[f_l] += x
 tot = sum(by.values()); tots = sum(st.values())
 print(f"total warp-instr {tot}  per frame {tot / frames:.0f}")
 for (f, l), n in by.most_common(45):
-    print(f"{f}:{l:<5d} {n / frames:10.1f}/frame {100 * n / tot:5.1f}%   stall samples {100 * st[(f, l)] / max(tots, 1):5.1f}%")
+    print(f"{f}:{l:<5d} {n / frames:10.1f}/frame {100 * n / tot:5.1f}%   stall samples {100 * st[(f, l)] / max(tots, 1):5.1f}%"
+          f"   smem wavefronts {wf[(f, l)] / frames:9.1f}/frame (excess {wx[(f, l)] / frames:8.1f})")
