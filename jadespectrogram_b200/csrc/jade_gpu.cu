@@ -23,6 +23,7 @@
 #include "jade_kernels.cuh"
 #include "jade_pk.cuh"
 #include "jade_pk_cta.cuh"
+#include "jade_pk_small.cuh"
 
 using jade::KParams;
 
@@ -54,6 +55,7 @@ kernel_fn cta_kernel(int R1, int mixk, bool general);             // jade_k_cta.
 kernel_fn pkcta_kernel(int R1, int mixk, bool want_db);           // jade_k_pkcta.cu
 kernel_fn pkcta2_kernel(int mixk);                                // jade_k_pkcta.cu
 kernel_fn pk2048_kernel(int mixk, bool want_db, bool guard);      // jade_k_pk.cu
+kernel_fn pksmall_kernel(int T, int mixk, bool want_db, bool guard); // jade_k_pksmall_a.cu / _b.cu
 } // namespace jade_k
 namespace {
 
@@ -187,18 +189,27 @@ int choose_kernel(jade_engine* e)
     const int N = e->N;
     const int mu = e->mixk;
     const bool po = e->general;
-    if (N == 2048 && !po && mu != jade::MIX_SEL) {
-        // headline path: packed-FP32x2 kernel (jade_pk.cuh)
+    if (N >= 128 && N <= 2048 && !po && mu != jade::MIX_SEL) {
+        // fast path: packed-FP32x2 kernels (jade_pk.cuh for N = 2048, jade_pk_small.cuh below)
+        const int T = N / 64;
         kc.family = 3;
         kc.threads = jade::PkCfg::WARPS * 32;
-        kc.units_per_block = jade::PkCfg::WARPS;
-        kc.smem = jade::PkCfg::smem_bytes(e->npal);
-        snprintf(kc.name, sizeof kc.name, "pk2048");
+        kc.units_per_block = jade::PkCfg::WARPS * (32 / T);
+        switch (T) {
+        case 2: kc.smem = jade::PkSmallCfg<2>::smem_bytes(e->npal); break;
+        case 4: kc.smem = jade::PkSmallCfg<4>::smem_bytes(e->npal); break;
+        case 8: kc.smem = jade::PkSmallCfg<8>::smem_bytes(e->npal); break;
+        case 16: kc.smem = jade::PkSmallCfg<16>::smem_bytes(e->npal); break;
+        default: kc.smem = jade::PkCfg::smem_bytes(e->npal); break;
+        }
+        if (T == 32) snprintf(kc.name, sizeof kc.name, "pk2048");
+        else snprintf(kc.name, sizeof kc.name, "pksmall<%d>", T);
         KernelChoice ke = kc; // boundary columns / unaligned geometries: same arithmetic, guarded loads
-        snprintf(ke.name, sizeof ke.name, "pk2048-guard");
-        kc.fn = jade_k::pk2048_kernel(mu, false, false);
-        kc.fn_db = jade_k::pk2048_kernel(mu, true, false);
-        ke.fn = jade_k::pk2048_kernel(mu, true, true);
+        snprintf(ke.name, sizeof ke.name, "%s-guard", kc.name);
+        kc.fn = T == 32 ? jade_k::pk2048_kernel(mu, false, false) : jade_k::pksmall_kernel(T, mu, false, false);
+        kc.fn_db = T == 32 ? jade_k::pk2048_kernel(mu, true, false) : jade_k::pksmall_kernel(T, mu, true, false);
+        ke.fn = T == 32 ? jade_k::pk2048_kernel(mu, true, true) : jade_k::pksmall_kernel(T, mu, true, true);
+        if (!kc.fn || !kc.fn_db || !ke.fn) return fail(e, JADE_ERR_ARG, "unsupported fft_size %d", N);
         ke.fn_db = nullptr;
         CU(e, cudaFuncSetAttribute((const void*)kc.fn_db, cudaFuncAttributeMaxDynamicSharedMemorySize, kc.smem));
         CU(e, cudaFuncSetAttribute((const void*)ke.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, ke.smem));

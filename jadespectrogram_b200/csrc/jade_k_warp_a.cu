@@ -8,8 +8,14 @@ kernel_fn pick(int mixk, bool general)
 {
     using namespace jade;
     if (mixk == MIX_SEL) return (kernel_fn)stft_warp_kernel<T, MIX_SEL, true>;
-    if (mixk == MIX_SUM) return general ? (kernel_fn)stft_warp_kernel<T, MIX_SUM, true> : (kernel_fn)stft_warp_kernel<T, MIX_SUM, false>;
-    return general ? (kernel_fn)stft_warp_kernel<T, MIX_NONE, true> : (kernel_fn)stft_warp_kernel<T, MIX_NONE, false>;
+    if constexpr (T >= 2) {
+        // N >= 128: the fast path is the packed kernel (jade_k_pk*.cu); only the general epilogue lives here
+        if (!general) return nullptr;
+        return mixk == MIX_SUM ? (kernel_fn)stft_warp_kernel<T, MIX_SUM, true> : (kernel_fn)stft_warp_kernel<T, MIX_NONE, true>;
+    } else {
+        if (mixk == MIX_SUM) return general ? (kernel_fn)stft_warp_kernel<T, MIX_SUM, true> : (kernel_fn)stft_warp_kernel<T, MIX_SUM, false>;
+        return general ? (kernel_fn)stft_warp_kernel<T, MIX_NONE, true> : (kernel_fn)stft_warp_kernel<T, MIX_NONE, false>;
+    }
 }
 } // namespace
 kernel_fn warp_kernel_small(int T, int mixk, bool general)

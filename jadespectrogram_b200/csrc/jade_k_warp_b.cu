@@ -8,8 +8,14 @@ kernel_fn pick(int mixk, bool general)
 {
     using namespace jade;
     if (mixk == MIX_SEL) return (kernel_fn)stft_warp_kernel<T, MIX_SEL, true>;
-    if (mixk == MIX_SUM) return general ? (kernel_fn)stft_warp_kernel<T, MIX_SUM, true> : (kernel_fn)stft_warp_kernel<T, MIX_SUM, false>;
-    return general ? (kernel_fn)stft_warp_kernel<T, MIX_NONE, true> : (kernel_fn)stft_warp_kernel<T, MIX_NONE, false>;
+    if constexpr (T >= 2) {
+        // N >= 128: the fast path is the packed kernel (jade_k_pk*.cu); only the general epilogue lives here
+        if (!general) return nullptr;
+        return mixk == MIX_SUM ? (kernel_fn)stft_warp_kernel<T, MIX_SUM, true> : (kernel_fn)stft_warp_kernel<T, MIX_NONE, true>;
+    } else {
+        if (mixk == MIX_SUM) return general ? (kernel_fn)stft_warp_kernel<T, MIX_SUM, true> : (kernel_fn)stft_warp_kernel<T, MIX_SUM, false>;
+        return general ? (kernel_fn)stft_warp_kernel<T, MIX_NONE, true> : (kernel_fn)stft_warp_kernel<T, MIX_NONE, false>;
+    }
 }
 } // namespace
 kernel_fn warp_kernel_small(int T, int mixk, bool general); // jade_k_warp_a.cu
@@ -17,11 +23,7 @@ kernel_fn warp_kernel(int T, int mixk, bool general)
 {
     switch (T) {
     case 16: return pick<16>(mixk, general);
-    case 32: // N = 2048: the fast path is stft_pk2048_kernel (jade_k_pk.cu); only the general epilogue lives here
-        if (!general && mixk != jade::MIX_SEL) return nullptr;
-        return mixk == jade::MIX_SEL ? (kernel_fn)jade::stft_warp_kernel<32, jade::MIX_SEL, true>
-             : mixk == jade::MIX_SUM ? (kernel_fn)jade::stft_warp_kernel<32, jade::MIX_SUM, true>
-                                     : (kernel_fn)jade::stft_warp_kernel<32, jade::MIX_NONE, true>;
+    case 32: return pick<32>(mixk, general);
     default: return warp_kernel_small(T, mixk, general);
     }
 }

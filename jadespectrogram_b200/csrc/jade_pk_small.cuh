@@ -1,0 +1,204 @@
+// jade_pk_small.cuh -- N = 64 T for T = 2, 4, 8, 16 (N = 128 ... 1024; BASELINE configs[0] is N = 1024) with the packed
+// FP32x2 arithmetic of jade_pk.cuh.  The plugin's GUI offers FFT sizes 512 ... 8192 (Spectrogram.cpp:413-417): 512 and
+// 1024 land here, 2048 in jade_pk.cuh, 4096 and 8192 in jade_pk_cta.cuh.
+//
+// T lanes transform one frame (F = 32 / T frames per warp), M = 32 T complex points z[m] = x[2m] + i x[2m+1], 32 per lane
+// (m = s + T n1, s = lane % T):
+//   pass 1 : radix-32 over n1 in registers (window fused into stage 1), twiddle W_M^(s k1);
+//   transpose inside the frame's T lanes through a padded shared-memory tile (32 rows of T+1);
+//   pass 2 : lane s owns rows k1 = s + T i (i < F) and runs F radix-T DFTs: u[i T + k2] = Z[(s + T i) + 32 k2];
+//   split  : pairs (k, M-k) with k2 < T/2: pair q = i T/2 + k2 of lane s has its partner in lane T - s, and the
+//            exchange tile is laid out so that it sits in row 15 - q, column T - s for EVERY lane: lane 0 (whose partners
+//            are its own values at irregular indices) files them into the extra column T itself;
+//   epilogue as in jade_pk.cuh.
+// Same reference lines replaced as jade_kernels.cuh (Spectrogram.cpp:50-56,137-145,64-107,634-647; CColorpalette.h:32-47).
+#pragma once
+#include "jade_pk.cuh"
+
+namespace jade {
+
+template <int T>
+struct PkSmallCfg {
+    static constexpr int M = 32 * T, N = 2 * M, B = M + 1;
+    static constexpr int F = 32 / T;
+    static constexpr int H = T / 2;   // k2 values per pair half
+    static constexpr int WARPS = 8;
+    static constexpr int ROW = 34;    // f2 words per s-row of the window / inter-pass twiddle tables (32 + 16 B pad)
+    static constexpr int PROW = 18;   // f2 words per s-row of the split-twiddle table (16 + 16 B pad)
+    // per-frame tile (f2 words): 32 rows of T+1 for the transpose, reused as 16 rows of T+1 for the exchange; the stride
+    // between the F tiles of a warp is kept == T (mod 16) so that frames sharing a half-warp hit disjoint banks
+    static constexpr int FS = 32 * (T + 1) + (T < 16 ? T : 0);
+    static constexpr int off_win = 0;
+    static constexpr int off_twI = off_win + T * ROW * 8;
+    static constexpr int off_twP = off_twI + T * ROW * 8;
+    static constexpr int off_pal = off_twP + T * PROW * 8;
+    static JADE_HD int off_xch(int npal) { return off_pal + (npal * 4 + 15) / 16 * 16; }
+    static JADE_HD int smem_bytes(int npal) { return off_xch(npal) + WARPS * F * FS * 8; }
+};
+
+// u-index of the value lane 0 pairs with its own pair q = i H + k2 (k = T i + 32 k2):  M - k lives in lane 0 as well
+template <int T>
+JADE_HD constexpr int lane0_partner(int q)
+{
+    constexpr int F = 32 / T, H = T / 2;
+    const int i = q / H, k2 = q % H;
+    return i >= 1 ? (F - i) * T + (T - 1 - k2) : (k2 >= 1 ? T - k2 : 0);
+}
+
+template <int T, int MIXK, bool WANT_DB, bool GUARD>
+JADE_KERNEL(PkSmallCfg<T>::WARPS * 32, 2) stft_pksmall_kernel(const KParams P)
+{
+    using Cfg = PkSmallCfg<T>;
+    constexpr int M = Cfg::M, F = Cfg::F, H = Cfg::H, FS = Cfg::FS, TS = T + 1;
+    static_assert(T >= 2 && T <= 16, "T = 32 is jade_pk.cuh");
+    JADE_DYN_SMEM(smem);
+    char* sm = reinterpret_cast<char*>(smem);
+    f2* s_win = reinterpret_cast<f2*>(sm + Cfg::off_win);
+    f2* s_twI = reinterpret_cast<f2*>(sm + Cfg::off_twI);
+    f2* s_twP = reinterpret_cast<f2*>(sm + Cfg::off_twP);
+    uint32_t* s_pal = reinterpret_cast<uint32_t*>(sm + Cfg::off_pal);
+    f2* s_xch = reinterpret_cast<f2*>(sm + Cfg::off_xch(P.npal));
+
+    // ---- per-s tables: entry (s, index) at [s*ROW + index]
+    for (int i = threadIdx.x; i < M; i += blockDim.x) {
+        const int s = i % T, n1 = i / T;                         // m = s + T n1
+        s_win[s * Cfg::ROW + n1] = pk(P.window[2 * i], P.window[2 * i + 1]);
+        const cpx t = P.twI[n1 * T + s];                         // W_M^(k1 s), k1 = n1 here
+        s_twI[s * Cfg::ROW + n1] = pk(t.x, t.y);
+    }
+    for (int i = threadIdx.x; i < 16 * T; i += blockDim.x) {
+        const int s = i % T, q = i / T;                          // pair q = ip H + k2: k = s + T ip + 32 k2
+        const cpx w = P.twP[s + T * (q / H) + 32 * (q % H)];     // W_N^k ; table holds -i W_N^k = (w.y, -w.x)
+        s_twP[s * Cfg::PROW + q] = pk(w.y, -w.x);
+    }
+    for (int i = threadIdx.x; i < P.npal; i += blockDim.x) s_pal[i] = P.palette[i];
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int f = lane / T, s = lane % T;
+    f2* xw = s_xch + (warp * F + f) * FS;
+    const f2x2* wrow = reinterpret_cast<const f2x2*>(s_win + s * Cfg::ROW);
+    const f2x2* trow = reinterpret_cast<const f2x2*>(s_twI + s * Cfg::ROW);
+    const f2x2* prow = reinterpret_cast<const f2x2*>(s_twP + s * Cfg::PROW);
+    f2* tr_wr = xw + s;               // transpose: word k1*TS + s
+    const f2* tr_rd = xw + s * TS;    //            row k1 = s + T i at tr_rd[T*i*TS + j]
+    f2* ex_wr = xw + s;               // exchange: row r(i', k2') = i' H + (k2' - H), word r*TS + s   (k2' >= H)
+    const f2* ex_rd = xw + (T - s);   // partner of pair q: row 15 - q, column T - s (lane 0: the extra column T)
+
+    const unsigned groups = (unsigned)((P.ncols + F - 1) / F);
+    const unsigned total = groups * (unsigned)P.nstreams;
+    int ch0, ch1;
+    channel_range(P, ch0, ch1);
+    const float scale = (MIXK == MIX_SUM) ? (1.0f / (float)P.channels) : 1.0f;
+
+    for (unsigned g = blockIdx.x * Cfg::WARPS + warp; g < total; g += gridDim.x * Cfg::WARPS) {
+        const int stream = (int)(g / groups);
+        int jrel = (int)(g - (unsigned)stream * groups) * F + f;
+        const bool active = jrel < P.ncols;
+        if (!active) jrel = P.ncols - 1; // transform the last column again, store nothing
+        const long long j = P.first_col + jrel;
+        const long long st = frame_start(P, j);
+
+        float alo[16], ahi[16], amid = 0.f; // bins k(q) = s + T i + 32 k2 / M - k(q) / M/2 (lane s = 0)
+#pragma unroll
+        for (int q = 0; q < 16; ++q) alo[q] = ahi[q] = 0.f;
+
+        for (int ch = ch0; ch < (MIXK == MIX_NONE ? ch0 + 1 : ch1); ++ch) {
+            const float* x = P.samples + stream * P.stream_stride + ch * P.channel_stride;
+            f2 v[32];
+#pragma unroll
+            for (int jj = 0; jj < 16; jj += 2) { // n1 = jj, jj+1 paired with n1 + 16
+                const f2x2 wa = wrow[jj / 2], wb = wrow[(jj + 16) / 2];
+                f2 xa0, xa1, xb0, xb1;
+                if (!GUARD) {
+                    const f2* xz = reinterpret_cast<const f2*>(x + st) + s;
+                    xa0 = xz[T * jj];
+                    xa1 = xz[T * (jj + 1)];
+                    xb0 = xz[T * (jj + 16)];
+                    xb1 = xz[T * (jj + 17)];
+                } else {
+                    const cpx a0 = load_pair_guarded(x, st + 2 * (s + T * jj), P.nsamples);
+                    const cpx a1 = load_pair_guarded(x, st + 2 * (s + T * (jj + 1)), P.nsamples);
+                    const cpx b0 = load_pair_guarded(x, st + 2 * (s + T * (jj + 16)), P.nsamples);
+                    const cpx b1 = load_pair_guarded(x, st + 2 * (s + T * (jj + 17)), P.nsamples);
+                    xa0 = pk(a0.x, a0.y);
+                    xa1 = pk(a1.x, a1.y);
+                    xb0 = pk(b0.x, b0.y);
+                    xb1 = pk(b1.x, b1.y);
+                }
+                win_stage1(v, jj, xa0, wa.a, xb0, wb.a);
+                win_stage1(v, jj + 1, xa1, wa.b, xb1, wb.b);
+            }
+            fft32_pk_after_stage1(v);
+#pragma unroll
+            for (int k1 = 0; k1 < 32; k1 += 2) {
+                const f2x2 t = trow[k1 / 2];
+                tr_wr[k1 * TS] = (k1 == 0) ? v[0] : cmul2(v[k1], t.a);
+                tr_wr[(k1 + 1) * TS] = cmul2(v[k1 + 1], t.b);
+            }
+            __syncwarp();
+            f2 u[32];
+#pragma unroll
+            for (int i = 0; i < F; ++i) {
+#pragma unroll
+                for (int jx = 0; jx < T; ++jx) u[i * T + brev(jx, ilog2c(T))] = tr_rd[T * i * TS + jx];
+                fft_pk<T>(u + i * T); // u[i T + k2] = Z[(s + T i) + 32 k2]
+            }
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < F; ++i)
+#pragma unroll
+                for (int k2 = H; k2 < T; ++k2) ex_wr[(i * H + (k2 - H)) * TS] = u[i * T + k2];
+            if (s == 0) { // lane 0 pairs with itself: file its partners into the extra column T (word r*TS + T)
+#pragma unroll
+                for (int q = 0; q < 16; ++q) xw[(15 - q) * TS + T] = u[lane0_partner<T>(q)];
+            }
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const int uq = (q / H) * T + (q % H);
+                const f2 zp = ex_rd[(15 - q) * TS];
+                const f2x2 wq = prow[q / 2];
+                const f2 A = add2(u[uq], conj2(zp));  // Z[k] + conj Z[M-k]
+                const f2 Bv = sub2(u[uq], conj2(zp)); // Z[k] - conj Z[M-k]
+                const f2 Tw = cmul2(Bv, (q & 1) ? wq.b : wq.a);
+                const f2 xp = add2(A, Tw), xm = sub2(A, Tw);
+                alo[q] = fm(lo(xp), lo(xp), fm(hi(xp), hi(xp), alo[q]));
+                ahi[q] = fm(lo(xm), lo(xm), fm(hi(xm), hi(xm), ahi[q]));
+            }
+            { // bin M/2 = 16 T (lane s = 0, i = 0, k2 = T/2; self-paired): X = 2 conj Z
+                const float a = lo(u[H]), b = hi(u[H]);
+                amid = fm(JADE_FMUL(4.0f, a), a, fm(JADE_FMUL(4.0f, b), b, amid));
+            }
+            __syncwarp();
+        }
+
+        const ColOut o = active ? col_out(P, stream, j) : ColOut{nullptr, nullptr};
+        // reference orientation: bin k lands in row M - k
+        uint32_t* p_lo = o.pix ? o.pix + (M - s) : nullptr; // bin k(q)   -> row M - k(q)
+        uint32_t* p_hi = o.pix ? o.pix + s : nullptr;       // bin M-k(q) -> row k(q)
+        float* d_lo = (WANT_DB && o.db) ? o.db + s : nullptr;
+        float* d_hi = (WANT_DB && o.db) ? o.db + (M - s) : nullptr;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const int koff = T * (q / H) + 32 * (q % H); // k(q) - s
+            const float dl = to_db_fast(MIXK == MIX_SUM ? JADE_FMUL(alo[q], scale) : alo[q]);
+            const float dh = to_db_fast(MIXK == MIX_SUM ? JADE_FMUL(ahi[q], scale) : ahi[q]);
+            if (WANT_DB && d_lo) {
+                d_lo[koff] = dl;
+                d_hi[-koff] = dh;
+            }
+            if (p_lo) {
+                p_lo[-koff] = colour_of(dl, P, s_pal);
+                p_hi[koff] = colour_of(dh, P, s_pal);
+            }
+        }
+        if (s == 0) {
+            const float dm = to_db_fast(MIXK == MIX_SUM ? JADE_FMUL(amid, scale) : amid);
+            if (WANT_DB && o.db) o.db[M / 2] = dm;
+            if (o.pix) o.pix[M / 2] = colour_of(dm, P, s_pal);
+        }
+    }
+}
+
+} // namespace jade

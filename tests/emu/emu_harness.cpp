@@ -6,6 +6,7 @@
 #include "../../jadespectrogram_b200/csrc/jade_kernels.cuh"
 #include "../../jadespectrogram_b200/csrc/jade_pk.cuh"
 #include "../../jadespectrogram_b200/csrc/jade_pk_cta.cuh"
+#include "../../jadespectrogram_b200/csrc/jade_pk_small.cuh"
 #include "../../jadespectrogram_b200/csrc/jade_host_tables.h"
 #include "../../include/jade_gpu.h"
 
@@ -38,6 +39,27 @@ void run_cta(const KParams& P, int mixk, bool general, int grid)
     else if (mixk == jade::MIX_SUM) jade_emu::launch(jade::stft_cta_kernel<R1, jade::MIX_SUM, false>, grid, block, smem, P);
     else if (general) jade_emu::launch(jade::stft_cta_kernel<R1, jade::MIX_NONE, true>, grid, block, smem, P);
     else jade_emu::launch(jade::stft_cta_kernel<R1, jade::MIX_NONE, false>, grid, block, smem, P);
+}
+// packed N <= 2048 kernels: T = 32 is jade_pk.cuh, smaller T jade_pk_small.cuh
+template <int T, int MIXK, bool WDB, bool GUARD>
+void run_pk_one(const KParams& P, int npal, int grid)
+{
+    const int block = jade::PkCfg::WARPS * 32;
+    if constexpr (T == 32) jade_emu::launch(jade::stft_pk2048_kernel<MIXK, WDB, GUARD>, grid, block, jade::PkCfg::smem_bytes(npal), P);
+    else jade_emu::launch(jade::stft_pksmall_kernel<T, MIXK, WDB, GUARD>, grid, block, jade::PkSmallCfg<T>::smem_bytes(npal), P);
+}
+template <int T>
+void run_pk(const KParams& P, int mixk, bool wdb, bool guard, int npal, int grid)
+{
+    if (mixk == jade::MIX_SUM) {
+        if (guard) run_pk_one<T, jade::MIX_SUM, true, true>(P, npal, grid);
+        else if (wdb) run_pk_one<T, jade::MIX_SUM, true, false>(P, npal, grid);
+        else run_pk_one<T, jade::MIX_SUM, false, false>(P, npal, grid);
+    } else {
+        if (guard) run_pk_one<T, jade::MIX_NONE, true, true>(P, npal, grid);
+        else if (wdb) run_pk_one<T, jade::MIX_NONE, true, false>(P, npal, grid);
+        else run_pk_one<T, jade::MIX_NONE, false, false>(P, npal, grid);
+    }
 }
 template <int R1>
 void run_pkcta(const KParams& P, int mixk, bool want_db, int npal, int grid)
@@ -119,9 +141,10 @@ extern "C" int emu_render(const jade_config* cin, const int32_t* palette, int np
     P.db_stream_stride = (long long)ncols * B;
     std::vector<jade::cpx> se;
     std::vector<float> sp;
-    if (N == 2048 && !general && multi != jade::MIX_SEL) {
-        // same routing as launch_stft in jade_gpu.cu: interior columns -> packed kernel, boundary columns -> warp<32>
-        jade_host::twiddle_matrix(1024, 32, 32, twI);
+    if (N >= 128 && N <= 2048 && !general && multi != jade::MIX_SEL) {
+        // same routing as launch_stft in jade_gpu.cu: interior columns -> packed kernel, boundary columns -> its guarded form
+        const int T = N / 64;
+        jade_host::twiddle_matrix(32 * T, 32, T, twI);
         P.twI = reinterpret_cast<const jade::cpx*>(twI.data());
         auto start = [&](long long j) {
             return (j / c.frames_per_block) * (long long)c.block_stride + (j % c.frames_per_block) * (long long)c.hop - c.preroll;
@@ -139,21 +162,19 @@ extern "C" int emu_render(const jade_config* cin, const int32_t* palette, int np
             if (Q.db) Q.db += (a - j0) * B;
             return Q;
         };
-        const int smem = jade::PkCfg::smem_bytes(npal);
-        const int block = jade::PkCfg::WARPS * 32;
-        if (hi > lo) {
-            const KParams Q = sub(lo, hi);
-            if (multi == jade::MIX_SUM && db) jade_emu::launch(jade::stft_pk2048_kernel<jade::MIX_SUM, true, false>, grid, block, smem, Q);
-            else if (multi == jade::MIX_SUM) jade_emu::launch(jade::stft_pk2048_kernel<jade::MIX_SUM, false, false>, grid, block, smem, Q);
-            else if (db) jade_emu::launch(jade::stft_pk2048_kernel<jade::MIX_NONE, true, false>, grid, block, smem, Q);
-            else jade_emu::launch(jade::stft_pk2048_kernel<jade::MIX_NONE, false, false>, grid, block, smem, Q);
-        }
-        for (int edge = 0; edge < 2; ++edge) {
-            const long long a = edge ? hi : j0, b = edge ? j1 : lo;
+        for (int part = 0; part < 3; ++part) {
+            const long long a = part == 0 ? lo : (part == 1 ? j0 : hi), b = part == 0 ? hi : (part == 1 ? lo : j1);
             if (b <= a) continue;
             const KParams Q = sub(a, b);
-            if (multi == jade::MIX_SUM) jade_emu::launch(jade::stft_pk2048_kernel<jade::MIX_SUM, true, true>, grid, block, smem, Q);
-            else jade_emu::launch(jade::stft_pk2048_kernel<jade::MIX_NONE, true, true>, grid, block, smem, Q);
+            const bool guard = part != 0, wdb = guard || db != nullptr;
+            switch (T) {
+            case 2: run_pk<2>(Q, multi, wdb, guard, npal, grid); break;
+            case 4: run_pk<4>(Q, multi, wdb, guard, npal, grid); break;
+            case 8: run_pk<8>(Q, multi, wdb, guard, npal, grid); break;
+            case 16: run_pk<16>(Q, multi, wdb, guard, npal, grid); break;
+            case 32: run_pk<32>(Q, multi, wdb, guard, npal, grid); break;
+            default: return -1;
+            }
         }
     } else if (N <= 2048) {
         const int T = N / 64;

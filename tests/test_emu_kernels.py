@@ -28,7 +28,8 @@ def _cfg(N, hop, ch, window, mix, **kw):
 CASES = [(64, 16, 1, "rect", "absmean"), (128, 32, 2, "hann", "absmean"), (256, 64, 1, "hamming", "absmean"),
          (512, 128, 3, "flattop", "absmean"), (1024, 512, 1, "hann", "absmean"), (2048, 512, 2, "hann", "absmean"),
          (2048, 256, 1, "hann", "min"), (1024, 205, 2, "hannpoisson", "max"), (2048, 512, 2, "hann", "right"),
-         (4096, 1024, 1, "hann", "absmean"), (16384, 4096, 1, "blackmanharris", "absmean"), (65536, 8192, 1, "hann", "absmean")]
+         (512, 128, 2, "hann", "absmean"), (512, 100, 1, "blackmanharris", "left"), (256, 63, 1, "hann", "absmean"),
+         (1024, 256, 4, "hann", "absmean"), (4096, 1024, 1, "hann", "absmean"), (16384, 4096, 1, "blackmanharris", "absmean"), (65536, 8192, 1, "hann", "absmean")]
 
 
 @pytest.mark.parametrize("N,hop,ch,window,mix", CASES)
