@@ -54,7 +54,7 @@ kernel_fn warp_kernel(int T, int mixk, bool general);             // jade_k_warp
 kernel_fn cta_kernel(int R1, int mixk, bool general);             // jade_k_cta.cu
 kernel_fn pkcta_kernel(int R1, int mixk, bool want_db);           // jade_k_pkcta.cu
 kernel_fn pkcta2_kernel(int mixk);                                // jade_k_pkcta.cu
-kernel_fn pk2048_kernel(int mixk, bool want_db, bool guard);      // jade_k_pk.cu
+kernel_fn pk2048_kernel(int mixk, bool want_db, int load);        // jade_k_pk.cu (load = jade::PK_LD_*)
 kernel_fn pksmall_kernel(int T, int mixk, bool want_db, bool guard); // jade_k_pksmall_a.cu / _b.cu
 } // namespace jade_k
 namespace {
@@ -122,6 +122,8 @@ struct jade_engine {
     int k_lo = 0, k_hi = 0;
     KernelChoice kc;
     KernelChoice kc_edge;  // family 3 only: guarded-load instantiation for boundary columns / unaligned geometries
+    KernelChoice kc_mid;   // N = 2048 only: LDG-to-register instantiation for 8- but not 16-byte aligned frames
+    bool has_mid = false;
     int mixk = 0;          // jade::MIX_NONE / MIX_SUM / MIX_SEL
     bool general = false;  // general (rolled) epilogue: pooled / cropped rows, precise dB, non-2^n channel mean, Max/Min
     bool pooled = false;
@@ -193,8 +195,9 @@ int choose_kernel(jade_engine* e)
         // fast path: packed-FP32x2 kernels (jade_pk.cuh for N = 2048, jade_pk_small.cuh below)
         const int T = N / 64;
         kc.family = 3;
-        kc.threads = jade::PkCfg::WARPS * 32;
-        kc.units_per_block = jade::PkCfg::WARPS * (32 / T);
+        const int warps = (T == 32) ? jade::PkCfg::WARPS : jade::PkSmallCfg<2>::WARPS;
+        kc.threads = warps * 32;
+        kc.units_per_block = warps * (32 / T);
         switch (T) {
         case 2: kc.smem = jade::PkSmallCfg<2>::smem_bytes(e->npal); break;
         case 4: kc.smem = jade::PkSmallCfg<4>::smem_bytes(e->npal); break;
@@ -206,10 +209,25 @@ int choose_kernel(jade_engine* e)
         else snprintf(kc.name, sizeof kc.name, "pksmall<%d>", T);
         KernelChoice ke = kc; // boundary columns / unaligned geometries: same arithmetic, guarded loads
         snprintf(ke.name, sizeof ke.name, "%s-guard", kc.name);
-        kc.fn = T == 32 ? jade_k::pk2048_kernel(mu, false, false) : jade_k::pksmall_kernel(T, mu, false, false);
-        kc.fn_db = T == 32 ? jade_k::pk2048_kernel(mu, true, false) : jade_k::pksmall_kernel(T, mu, true, false);
-        ke.fn = T == 32 ? jade_k::pk2048_kernel(mu, true, true) : jade_k::pksmall_kernel(T, mu, true, true);
+        kc.fn = T == 32 ? jade_k::pk2048_kernel(mu, false, jade::PK_LD_ASYNC) : jade_k::pksmall_kernel(T, mu, false, false);
+        kc.fn_db = T == 32 ? jade_k::pk2048_kernel(mu, true, jade::PK_LD_ASYNC) : jade_k::pksmall_kernel(T, mu, true, false);
+        ke.fn = T == 32 ? jade_k::pk2048_kernel(mu, true, jade::PK_LD_GUARD) : jade_k::pksmall_kernel(T, mu, true, true);
         if (!kc.fn || !kc.fn_db || !ke.fn) return fail(e, JADE_ERR_ARG, "unsupported fft_size %d", N);
+        e->has_mid = false;
+        if (T == 32) {
+            KernelChoice km = kc;
+            snprintf(km.name, sizeof km.name, "pk2048-ldg");
+            km.fn = jade_k::pk2048_kernel(mu, false, jade::PK_LD_DIRECT);
+            km.fn_db = jade_k::pk2048_kernel(mu, true, jade::PK_LD_DIRECT);
+            CU(e, cudaFuncSetAttribute((const void*)km.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, km.smem));
+            CU(e, cudaFuncSetAttribute((const void*)km.fn_db, cudaFuncAttributeMaxDynamicSharedMemorySize, km.smem));
+            int occ_m = 0;
+            CU(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_m, (const void*)km.fn, km.threads, km.smem));
+            if (occ_m < 1) return fail(e, JADE_ERR_CUDA, "kernel %s does not fit on an SM (smem %d)", km.name, km.smem);
+            km.blocks_per_sm = occ_m;
+            e->kc_mid = km;
+            e->has_mid = true;
+        }
         ke.fn_db = nullptr;
         CU(e, cudaFuncSetAttribute((const void*)kc.fn_db, cudaFuncAttributeMaxDynamicSharedMemorySize, kc.smem));
         CU(e, cudaFuncSetAttribute((const void*)ke.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, ke.smem));
@@ -384,8 +402,11 @@ int launch_stft(jade_engine* e, KParams& P, cudaStream_t st)
 {
     if ((long long)P.ncols * P.nstreams <= 0) return 0;
     if (e->kc.family != 3) return launch_one(e, e->kc, P, st);
-    // packed N = 2048 kernel: interior, 8-byte aligned frames; the rest goes to its guarded-load instantiation
+    // packed kernels: interior, aligned frames (16 bytes: cp.async staging for N = 2048; 8 bytes: LDG.64); the rest goes
+    // to the guarded-load instantiation
     if (!P.aligned2) return launch_one(e, e->kc_edge, P, st);
+    static const bool force_ldg = [] { const char* v = getenv("JADE_PK_LOAD"); return v && !strcmp(v, "ldg"); }(); // experiments
+    const KernelChoice& main_kc = (e->has_mid && (!P.aligned4 || force_ldg)) ? e->kc_mid : e->kc;
     const long long j0 = P.first_col, j1 = P.first_col + P.ncols;
     auto start = [&](long long j) { return frame_start_abs(e->cfg, j) - P.sample_base; };
     long long lo = j0, hi = j1;
@@ -393,7 +414,7 @@ int launch_stft(jade_engine* e, KParams& P, cudaStream_t st)
     while (hi > lo && start(hi - 1) + e->N > P.nsamples) --hi;
     if (hi > lo) {
         KParams Q = sub_range(e, P, lo, hi);
-        if (int r = launch_one(e, e->kc, Q, st)) return r;
+        if (int r = launch_one(e, main_kc, Q, st)) return r;
     }
     if (lo > j0) {
         KParams Q = sub_range(e, P, j0, lo);
@@ -882,6 +903,8 @@ int jade_push_samples(jade_engine* e, const float* const* planar, int nch, int n
             P.sample_base = e->hist_base_abs;
             P.aligned2 = ((e->hist_cap % 2) == 0 && (c.hop % 2) == 0 && (c.block_stride % 2) == 0 &&
                           (c.preroll % 2) == 0 && (e->hist_base_abs % 2) == 0) ? 1 : 0;
+            P.aligned4 = ((e->hist_cap % 4) == 0 && (c.hop % 4) == 0 && (c.block_stride % 4) == 0 &&
+                          (c.preroll % 4) == 0 && (e->hist_base_abs % 4) == 0 && ((uintptr_t)e->d_hist.p % 16) == 0) ? 1 : 0;
             P.first_col = j0;
             P.ncols = (int)n;
             P.nstreams = 1;
@@ -1006,6 +1029,8 @@ int jade_render_device(jade_engine* e, const float* d_samples, int nstreams, int
     P.sample_base = 0;
     P.aligned2 = ((stream_stride % 2) == 0 && (channel_stride % 2) == 0 && (c.hop % 2) == 0 && (c.block_stride % 2) == 0 &&
                   (c.preroll % 2) == 0 && ((uintptr_t)d_samples % 8) == 0) ? 1 : 0;
+    P.aligned4 = ((stream_stride % 4) == 0 && (channel_stride % 4) == 0 && (c.hop % 4) == 0 && (c.block_stride % 4) == 0 &&
+                  (c.preroll % 4) == 0 && ((uintptr_t)d_samples % 16) == 0) ? 1 : 0;
     P.first_col = first_col;
     P.ncols = (int)ncols;
     P.nstreams = nstreams;
@@ -1105,10 +1130,10 @@ int jade_render_batch(jade_engine* e, const float* samples, int nstreams, int64_
             cudaStream_t st = e->pipe_stream[slot];
             // sample range needed by columns [first_col+c0, first_col+c0+nc)
             long long a = frame_start_abs(c, first_col + c0), b = frame_start_abs(c, first_col + c0 + nc - 1) + N;
-            a = std::max<long long>(0, a) & ~1LL;
+            a = std::max<long long>(0, a) & ~3LL; // 16-byte aligned chunk origin (cp.async staging in the N = 2048 kernel)
             b = std::min<long long>(nsamples, b);
             long long len = std::max<long long>(0, b - a);
-            const long long len_pad = (len + 1) & ~1LL;
+            const long long len_pad = (len + 3) & ~3LL;
             const size_t in_bytes = (size_t)ns * C * len_pad * 4;
             if (e->pipe_in[slot].ensure(std::max<size_t>(in_bytes, 16))) return fail(e, JADE_ERR_CUDA, "device input allocation failed");
             if (len > 0) {
@@ -1135,6 +1160,7 @@ int jade_render_batch(jade_engine* e, const float* samples, int nstreams, int64_
             P.nsamples = len;
             P.sample_base = a;
             P.aligned2 = ((c.hop % 2) == 0 && (c.block_stride % 2) == 0 && (c.preroll % 2) == 0) ? 1 : 0;
+            P.aligned4 = ((c.hop % 4) == 0 && (c.block_stride % 4) == 0 && (c.preroll % 4) == 0) ? 1 : 0;
             P.first_col = first_col + c0;
             P.ncols = (int)nc;
             P.nstreams = ns;

@@ -2,14 +2,20 @@
 #include "jade_pk.cuh"
 namespace jade_k {
 typedef void (*kernel_fn)(const jade::KParams);
-kernel_fn pk2048_kernel(int mixk, bool want_db, bool guard)
+// load: jade::PK_LD_ASYNC (cp.async staging, 16-byte aligned interior frames), PK_LD_DIRECT (8-byte aligned interior
+// frames), PK_LD_GUARD (bounds-checked; always the dB-storing form)
+kernel_fn pk2048_kernel(int mixk, bool want_db, int load)
 {
     using namespace jade;
     if (mixk == MIX_SUM) {
-        if (guard) return (kernel_fn)stft_pk2048_kernel<MIX_SUM, true, true>;
-        return want_db ? (kernel_fn)stft_pk2048_kernel<MIX_SUM, true, false> : (kernel_fn)stft_pk2048_kernel<MIX_SUM, false, false>;
+        if (load == PK_LD_GUARD) return (kernel_fn)stft_pk2048_kernel<MIX_SUM, true, PK_LD_GUARD>;
+        if (load == PK_LD_DIRECT)
+            return want_db ? (kernel_fn)stft_pk2048_kernel<MIX_SUM, true, PK_LD_DIRECT> : (kernel_fn)stft_pk2048_kernel<MIX_SUM, false, PK_LD_DIRECT>;
+        return want_db ? (kernel_fn)stft_pk2048_kernel<MIX_SUM, true, PK_LD_ASYNC> : (kernel_fn)stft_pk2048_kernel<MIX_SUM, false, PK_LD_ASYNC>;
     }
-    if (guard) return (kernel_fn)stft_pk2048_kernel<MIX_NONE, true, true>;
-    return want_db ? (kernel_fn)stft_pk2048_kernel<MIX_NONE, true, false> : (kernel_fn)stft_pk2048_kernel<MIX_NONE, false, false>;
+    if (load == PK_LD_GUARD) return (kernel_fn)stft_pk2048_kernel<MIX_NONE, true, PK_LD_GUARD>;
+    if (load == PK_LD_DIRECT)
+        return want_db ? (kernel_fn)stft_pk2048_kernel<MIX_NONE, true, PK_LD_DIRECT> : (kernel_fn)stft_pk2048_kernel<MIX_NONE, false, PK_LD_DIRECT>;
+    return want_db ? (kernel_fn)stft_pk2048_kernel<MIX_NONE, true, PK_LD_ASYNC> : (kernel_fn)stft_pk2048_kernel<MIX_NONE, false, PK_LD_ASYNC>;
 }
 } // namespace jade_k

@@ -69,6 +69,7 @@ struct KParams {
     long long nsamples;     // valid samples per channel; reads outside [0,nsamples) give 0
     long long sample_base;  // absolute sample index of samples[..][0]
     int aligned2;           // every frame start is even and the channel bases are 8-byte aligned
+    int aligned4;           // every frame start is a multiple of 4 samples and the channel bases are 16-byte aligned
     // ---- geometry: column j starts at (j / fb) * bstride + (j % fb) * hop - preroll   (absolute sample index)
     int N, M, B;
     int hop, fb, bstride, preroll;

@@ -178,49 +178,266 @@ JADE_DEVICE void win_stage1(f2* v, int j, f2 xa, f2 wa, f2 xb, f2 wb)
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// asynchronous global -> shared copy (LDGSTS) and the 64-bit lane shuffle
+// ---------------------------------------------------------------------------------------------------------
+#if defined(JADE_EMU)
+inline void cp_async16(void* dst, const void* src) { std::memcpy(dst, src, 16); }
+inline void cp_async_wait_all() {}
+inline f2 shfl2(f2 v, int src_lane)
+{
+    unsigned long long b;
+    std::memcpy(&b, &v, 8);
+    b = __shfl_sync(0xffffffffu, b, src_lane);
+    std::memcpy(&v, &b, 8);
+    return v;
+}
+inline f2 sel2(bool c, f2 a, f2 b) { return c ? a : b; }
+#else
+__device__ __forceinline__ void cp_async16(void* dst, const void* src)
+{
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(dst);
+    // .cg: L2 only -- the 4x frame overlap is served by L2; measured faster than .ca (gpurun_out/variants4.txt)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ f2 shfl2(f2 v, int src_lane) { return __shfl_sync(0xffffffffu, v, src_lane); }
+__device__ __forceinline__ f2 sel2(bool c, f2 a, f2 b) { return c ? a : b; }
+#endif
+
+// Bulk asynchronous copy (TMA, cp.async.bulk / UBLKCP): one lane moves a whole 8 KB frame, completion is signalled on a
+// per-warp mbarrier.  The bytes reach shared memory through the async proxy, not through LSU instructions.
+#if defined(JADE_EMU)
+inline void mbar_init(unsigned long long*, int) {}
+inline void bulk_copy_g2s(void* dst, const void* src, int bytes, unsigned long long*) { std::memcpy(dst, src, (size_t)bytes); }
+inline void mbar_wait(unsigned long long*, unsigned) {}
+#else
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count)
+{
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // visible to the async proxy (the __syncthreads follows)
+}
+// executed by ONE lane after a __syncwarp(): earlier generic-proxy accesses of the warp to dst are ordered before the copy
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, int bytes, unsigned long long* bar)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst), b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d), "l"(src),
+                 "r"(bytes), "r"(b)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
+{
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("{\n"
+                 ".reg .pred p;\n"
+                 "WAIT_%=:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 "@p bra DONE_%=;\n"
+                 "bra WAIT_%=;\n"
+                 "DONE_%=:\n"
+                 "}" ::"r"(b), "r"(parity)
+                 : "memory");
+}
+#endif
+
+// ---------------------------------------------------------------------------------------------------------
+// Pass 2 with the inter-pass twiddle folded into the butterflies ("twisted" DIT).  After the transpose lane k1 holds
+// y[j] (j = n2 = 0..31) and needs  Z[k1 + 32 k2] = sum_j y[j] u^j W_32^{j k2},  u = W_1024^{k1}.  Writing the DIT recursion
+// for the polynomial in (u W_32^{k2}) gives the ordinary radix-2 flow graph whose stage of length LEN uses
+//     u^{32/LEN} W_LEN^J = W_1024^{(32/LEN)(k1 + 32 J)},   J = 0 .. LEN/2-1,
+// instead of W_LEN^J.  J >= LEN/4 is -i times entry J - LEN/4, so a lane needs 1+1+2+4+8 = 16 table values per
+// transform instead of 31 separate twiddle factors, the 31 complex multiplies disappear, and every butterfly is the
+// 3-instruction FFMA2 form.  Each table value is one correctly rounded root of unity (from P.twP).
+// ---------------------------------------------------------------------------------------------------------
+// a' = a + W b, b' = a - W b with W = (wr, wi) held in registers
+JADE_DEVICE void bfly_w(f2& a, f2& b, f2 w)
+{
+    const float wr = lo(w), wi = hi(w);
+    const f2 n = fma2(mul_pi(b), pk(wi, wi), fma2(b, pk(wr, wr), a)); // a + wr b + wi (i b)
+    b = fma2(a, pk(2.0f, 2.0f), neg2(n));
+    a = n;
+}
+// the same with W = -i (wr, wi) = (wi, -wr)
+JADE_DEVICE void bfly_wmi(f2& a, f2& b, f2 w)
+{
+    const float wr = lo(w), wi = hi(w);
+    const f2 n = fma2(mul_mi(b), pk(wr, wr), fma2(b, pk(wi, wi), a)); // a + wi b + wr (-i b)
+    b = fma2(a, pk(2.0f, 2.0f), neg2(n));
+    a = n;
+}
+template <int LEN, int BASE, int J>
+JADE_DEVICE void tw_inner(f2* a, const f2* tw)
+{
+    if constexpr (J < LEN / 2) {
+        constexpr int Q = (LEN >= 4) ? LEN / 4 : 1;
+        if constexpr (J < Q) bfly_w(a[BASE + J], a[BASE + J + LEN / 2], tw[J]);
+        else bfly_wmi(a[BASE + J], a[BASE + J + LEN / 2], tw[J - Q]);
+        tw_inner<LEN, BASE, J + 1>(a, tw);
+    }
+}
+template <int LEN, int BASE>
+JADE_DEVICE void tw_blocks(f2* a, const f2* tw)
+{
+    if constexpr (BASE < 32) {
+        tw_inner<LEN, BASE, 0>(a, tw);
+        tw_blocks<LEN, BASE + LEN>(a, tw);
+    }
+}
+// (Computing eleven of the sixteen values as base x constant instead -- 5 table reads and 22 extra FMUL2/FFMA2 per
+// transform, and likewise the split twiddles from one base -- removes 14 % of the shared-memory wavefronts but was 2 %
+// slower: the FP32 pipe is the scarcer resource, gpurun_out/variants7.txt.)
+template <int J0>
+JADE_DEVICE void tw32_half(f2* u, const f2x2 ta, const f2x2 tb)
+{
+    const f2 w[4] = {ta.a, ta.b, tb.a, tb.b};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        bfly_w(u[J0 + i], u[J0 + i + 16], w[i]);
+        bfly_wmi(u[J0 + i + 8], u[J0 + i + 24], w[i]);
+    }
+}
+// exponent e of table entry t (0..15) of lane k1: the entry is W_1024^e
+JADE_HD int tw2_exponent(int k1, int t)
+{
+    if (t == 0) return 16 * k1;                  // LEN 2
+    if (t == 1) return 8 * k1;                   // LEN 4
+    if (t < 4) return 4 * (k1 + 32 * (t - 2));   // LEN 8,  J = 0,1
+    if (t < 8) return 2 * (k1 + 32 * (t - 4));   // LEN 16, J = 0..3
+    return k1 + 32 * (t - 8);                    // LEN 32, J = 0..7
+}
+// in-place twisted 32-point pass: bit-reversed input, natural-order output; trow = this lane's 16 table values
+JADE_DEVICE void fft32_twisted(f2* u, const f2x2* trow)
+{
+    {
+        const f2x2 t = trow[0];
+        tw_blocks<2, 0>(u, &t.a);
+        tw_blocks<4, 0>(u, &t.b);
+    }
+    {
+        const f2x2 t = trow[1];
+        const f2 w[2] = {t.a, t.b};
+        tw_blocks<8, 0>(u, w);
+    }
+    {
+        const f2x2 t0 = trow[2], t1 = trow[3];
+        const f2 w[4] = {t0.a, t0.b, t1.a, t1.b};
+        tw_blocks<16, 0>(u, w);
+    }
+    // LEN 32 in two halves (entries J = 0..3, then 4..7; J + 8 is -i times entry J) so that only four twiddles are live
+    tw32_half<0>(u, trow[4], trow[5]);
+    tw32_half<4>(u, trow[6], trow[7]);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// occupancy: JADE_PK_WARPS warps per CTA, JADE_PK_CTAS CTAs per SM (register cap = 65536 / (32 WARPS CTAS))
+#ifndef JADE_PK_WARPS
+#define JADE_PK_WARPS 12
+#endif
+#ifndef JADE_PK_CTAS
+#define JADE_PK_CTAS 1
+#endif
 struct PkCfg {
     static constexpr int M = 1024, N = 2048, B = 1025;
-    static constexpr int WARPS = 8;
-    static constexpr int ROW = 34;   // f2 words per lane row of the window / inter-pass twiddle tables (32 + 16 B pad)
+    static constexpr int WARPS = JADE_PK_WARPS;
+    static constexpr int ROW = 34;   // f2 words per lane row of the window table (32 + 16 B pad)
+    static constexpr int TROW = 18;  // f2 words per lane row of the twisted pass-2 table (16 + 16 B pad)
     static constexpr int PROW = 18;  // f2 words per lane row of the split-twiddle table (16 + 16 B pad)
-    static constexpr int XCH = 32 * 33; // f2 words per warp exchange buffer (transpose: 32 rows of 33)
+    static constexpr int XROW = 34;  // f2 words per transpose row: 16-byte aligned rows, conflict-free LDS.128
+    static constexpr int XCH = 32 * XROW; // f2 words per warp buffer: transpose, and landing area of the next frame (1024)
     static constexpr int off_win = 0;
-    static constexpr int off_twI = off_win + 32 * ROW * 8;
-    static constexpr int off_twP = off_twI + 32 * ROW * 8;
+    static constexpr int off_tw2 = off_win + 32 * ROW * 8;
+    static constexpr int off_twP = off_tw2 + 32 * TROW * 8;
     static constexpr int off_pal = off_twP + 32 * PROW * 8;
-    static JADE_HD int off_xch(int npal) { return off_pal + (npal * 4 + 15) / 16 * 16; }
+    static JADE_HD int off_bar(int npal) { return off_pal + (npal * 4 + 15) / 16 * 16; } // one mbarrier per warp
+    static JADE_HD int off_xch(int npal) { return off_bar(npal) + (WARPS * 8 + 15) / 16 * 16; }
     static JADE_HD int smem_bytes(int npal) { return off_xch(npal) + WARPS * XCH * 8; }
 };
 
-// GUARD = false: frames must lie entirely inside [0, nsamples) and start on an even sample (8-byte aligned float2
-// loads).  The host (launch_stft in jade_gpu.cu) sends the few columns that touch the signal boundary, and unaligned
-// geometries, to the GUARD = true instantiation: bounds-checked scalar loads, bit-identical arithmetic afterwards (so
-// streaming, batch and sharded renderings of the same column agree bit for bit whichever instantiation produced it).
+// How a frame reaches the registers:
+//   PK_LD_ASYNC  : frames lie inside [0, nsamples) and start on a multiple of 4 samples with 16-byte aligned channel
+//                  bases (P.aligned4).  Each warp copies the NEXT channel / frame it will transform into its own
+//                  buffer with cp.async (LDGSTS.128, no registers, no waiting) right after the transpose of the current
+//                  one has been read back, so the global-memory latency is covered by pass 2, the split and the
+//                  epilogue (profiles/r01e: 17.5 % of all warp stalls were the first use of a global load).
+//   PK_LD_DIRECT : interior frames on an even sample (P.aligned2): LDG.64 straight to registers.
+//   PK_LD_GUARD  : bounds-checked scalar loads for the few columns that touch the signal boundary, and unaligned
+//                  geometries; routed by launch_stft in jade_gpu.cu.
+// The arithmetic after the load is the same code in all three, so streaming, batch and sharded renderings of a column
+// agree bit for bit whichever instantiation produced it.
+enum { PK_LD_ASYNC = 0, PK_LD_DIRECT = 1, PK_LD_GUARD = 2 };
+
+struct PkUnit {
+    int stream;
+    long long j, st;
+};
+JADE_DEVICE PkUnit pk_unit(const KParams& P, unsigned g)
+{
+    PkUnit u;
+    u.stream = (int)(g / (unsigned)P.ncols);
+    u.j = P.first_col + (g - (unsigned)u.stream * (unsigned)P.ncols);
+    u.st = frame_start(P, u.j);
+    return u;
+}
+// 8 KB of one channel's frame -> the warp buffer.  Default: one bulk copy issued by lane 0 (call after a __syncwarp()).
+// -DJADE_PK_LDGSTS: 16 x LDGSTS.128 per lane instead (512 contiguous bytes per instruction).
+JADE_DEVICE void pk_prefetch(f2* xw, const float* src, int s, unsigned long long* bar)
+{
+#if defined(JADE_PK_LDGSTS)
+    char* d = reinterpret_cast<char*>(xw) + 16 * s;
+    const char* g = reinterpret_cast<const char*>(src) + 16 * s;
+#pragma unroll
+    for (int t = 0; t < 16; ++t) cp_async16(d + 512 * t, g + 512 * t);
+#else
+    if (s == 0) bulk_copy_g2s(xw, src, PkCfg::M * 8, bar);
+#if defined(JADE_EMU)
+    __syncwarp();
+#endif
+#endif
+}
+// wait for the copy started by the last pk_prefetch of this warp; parity = number of completed copies & 1
+JADE_DEVICE void pk_prefetch_wait(unsigned long long* bar, unsigned parity)
+{
+#if defined(JADE_PK_LDGSTS)
+    cp_async_wait_all();
+    __syncwarp();
+#else
+    mbar_wait(bar, parity);
+#endif
+}
+
 // MIXK: MIX_NONE (one contributing channel) or MIX_SUM (AbsMean over 2^n channels).  Identity rows in the reference
 // orientation, hardware log2 for the dB.  WANT_DB additionally stores the float dB column (streaming ring / getMem).
-template <int MIXK, bool WANT_DB, bool GUARD>
-JADE_KERNEL(PkCfg::WARPS * 32, 2) stft_pk2048_kernel(const KParams P)
+template <int MIXK, bool WANT_DB, int LD>
+#if defined(JADE_PK_MAXREG) && !defined(JADE_EMU)
+__global__ void __maxnreg__(JADE_PK_MAXREG) stft_pk2048_kernel(const KParams P)
+#else
+JADE_KERNEL(PkCfg::WARPS * 32, JADE_PK_CTAS) stft_pk2048_kernel(const KParams P)
+#endif
 {
     using Cfg = PkCfg;
     constexpr int M = Cfg::M;
     JADE_DYN_SMEM(smem);
     char* sm = reinterpret_cast<char*>(smem);
     f2* s_win = reinterpret_cast<f2*>(sm + Cfg::off_win);
-    f2* s_twI = reinterpret_cast<f2*>(sm + Cfg::off_twI);
+    f2* s_tw2 = reinterpret_cast<f2*>(sm + Cfg::off_tw2);
     f2* s_twP = reinterpret_cast<f2*>(sm + Cfg::off_twP);
     uint32_t* s_pal = reinterpret_cast<uint32_t*>(sm + Cfg::off_pal);
+    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(sm + Cfg::off_bar(P.npal));
     f2* s_xch = reinterpret_cast<f2*>(sm + Cfg::off_xch(P.npal));
 
     // ---- per-lane tables: entry for (lane s, index i) at [s*ROW + i]
     for (int i = threadIdx.x; i < M; i += blockDim.x) {
         const int s = i & 31, n1 = i >> 5;                       // m = s + 32 n1
         s_win[s * Cfg::ROW + n1] = pk(P.window[2 * i], P.window[2 * i + 1]);
-        const cpx t = P.twI[n1 * 32 + s];                        // W_1024^(k1 s), k1 = n1 here
-        s_twI[s * Cfg::ROW + n1] = pk(t.x, t.y);
     }
+    if (LD == PK_LD_ASYNC && threadIdx.x < Cfg::WARPS) mbar_init(s_bar + threadIdx.x, 1);
     for (int i = threadIdx.x; i < 512; i += blockDim.x) {
-        const int s = i & 31, q = i >> 5;                        // k = s + 32 q
-        const cpx w = P.twP[s + 32 * q];                         // W_N^k ; table holds -i W_N^k = (w.y, -w.x)
+        const int s = i & 31, q = i >> 5;
+        const cpx t = P.twP[2 * tw2_exponent(s, q)];             // W_1024^e = W_2048^{2e}
+        s_tw2[s * Cfg::TROW + q] = pk(t.x, t.y);
+        const cpx w = P.twP[s + 32 * q];                         // k = s + 32 q: table holds -i W_N^k = (w.y, -w.x)
         s_twP[s * Cfg::PROW + q] = pk(w.y, -w.x);
     }
     for (int i = threadIdx.x; i < P.npal; i += blockDim.x) s_pal[i] = P.palette[i];
@@ -228,112 +445,149 @@ JADE_KERNEL(PkCfg::WARPS * 32, 2) stft_pk2048_kernel(const KParams P)
 
     const int s = threadIdx.x & 31, warp = threadIdx.x >> 5;
     f2* xw = s_xch + warp * Cfg::XCH;
+    unsigned long long* bar = s_bar + warp;
+    unsigned copies = 0; // bulk copies of this warp waited for so far (mbarrier phase parity)
     const f2x2* wrow = reinterpret_cast<const f2x2*>(s_win + s * Cfg::ROW);
-    const f2x2* trow = reinterpret_cast<const f2x2*>(s_twI + s * Cfg::ROW);
+    const f2x2* trow = reinterpret_cast<const f2x2*>(s_tw2 + s * Cfg::TROW);
     const f2x2* prow = reinterpret_cast<const f2x2*>(s_twP + s * Cfg::PROW);
-    f2* tr_wr = xw + s;            // transpose: word k1*33 + s
-    const f2* tr_rd = xw + s * 33; //            row s, words j
-    f2* ex_wr = xw + s;            // exchange: word (i-16)*32 + s holds Z[s + 32 i], i = 16..31; row 16 holds Z[s]
-    const f2* ex_rd = xw + (32 - s); // partner of k = s + 32 q is word (15-q)*32 + (32-s)   (lane 0: its own column)
+    f2* tr_wr = xw + s;                                                      // transpose: word k1*XROW + s
+    const f2x2* tr_rd = reinterpret_cast<const f2x2*>(xw + s * Cfg::XROW);   //            row s, words j (two per load)
+    const int partner = (32 - s) & 31; // lane holding Z[M - k] for this lane's k = s + 32 q  (lane 0: itself)
 
     const unsigned total = (unsigned)P.ncols * (unsigned)P.nstreams;
+    const unsigned gstep = gridDim.x * Cfg::WARPS;
     int ch0, ch1;
     channel_range(P, ch0, ch1);
+    if (MIXK == MIX_NONE) ch1 = ch0 + 1;
     const float scale = (MIXK == MIX_SUM) ? (1.0f / (float)P.channels) : 1.0f;
 
-    for (unsigned g = blockIdx.x * Cfg::WARPS + warp; g < total; g += gridDim.x * Cfg::WARPS) {
-        const int stream = (int)(g / (unsigned)P.ncols);
-        const long long j = P.first_col + (g - (unsigned)stream * (unsigned)P.ncols);
-        const long long st = frame_start(P, j);
+    // One column: dB, palette, packed pixel (and the dB value for the streaming ring).  Reference orientation: bin k lands
+    // in row M - k, so lane s writes rows M-s-32q (bins s+32q) and rows s+32q (bins M-s-32q): both coalesced.
+    auto emit = [&](float p, uint32_t* pix, float* db) {
+        const float d = to_db_fast(MIXK == MIX_SUM ? JADE_FMUL(p, scale) : p);
+        if (WANT_DB) {
+            if (db) *db = d;
+            if (pix) *pix = colour_of(d, P, s_pal);
+        } else {
+            *pix = colour_of(d, P, s_pal); // the plain instantiation is only launched with a pixel buffer
+        }
+    };
 
-        float alo[16], ahi[16], amid = 0.f; // power of bins s+32q / M-(s+32q) / 512 (lane 0)
+    unsigned g = blockIdx.x * Cfg::WARPS + warp;
+    if (LD == PK_LD_ASYNC && g < total) {
+        const PkUnit un = pk_unit(P, g);
+        pk_prefetch(xw, P.samples + un.stream * P.stream_stride + ch0 * P.channel_stride + un.st, s, bar);
+    }
+    for (; g < total; g += gstep) {
+        const PkUnit un = pk_unit(P, g);
+        const ColOut o = col_out(P, un.stream, un.j);
+        const float* x = P.samples + un.stream * P.stream_stride + ch0 * P.channel_stride + un.st; // frame, channel ch
+
+        float alo[16], ahi[16], amid = 0.f; // power of bins s+32q / M-(s+32q) / 512 (lane 0) of the channels so far
 #pragma unroll
         for (int q = 0; q < 16; ++q) alo[q] = ahi[q] = 0.f;
 
-        for (int ch = ch0; ch < (MIXK == MIX_NONE ? ch0 + 1 : ch1); ++ch) {
-            const float* x = P.samples + stream * P.stream_stride + ch * P.channel_stride;
+        for (int ch = ch0; ch < ch1; ++ch, x += P.channel_stride) {
+            const bool last = (MIXK == MIX_NONE) || (ch + 1 == ch1);
             f2 v[32];
+            if (LD == PK_LD_ASYNC) {
+                pk_prefetch_wait(bar, copies & 1u);
+                ++copies;
+            }
 #pragma unroll
-            for (int j = 0; j < 16; j += 2) { // n1 = j, j+1 paired with n1 + 16
-                const f2x2 wa = wrow[j / 2], wb = wrow[(j + 16) / 2];
+            for (int jj = 0; jj < 16; jj += 2) { // n1 = jj, jj+1 paired with n1 + 16
+                const f2x2 wa = wrow[jj / 2], wb = wrow[(jj + 16) / 2];
                 f2 xa0, xa1, xb0, xb1;
-                if (!GUARD) {
-                    const f2* xz = reinterpret_cast<const f2*>(x + st) + s;
-                    xa0 = xz[32 * j];
-                    xa1 = xz[32 * (j + 1)];
-                    xb0 = xz[32 * (j + 16)];
-                    xb1 = xz[32 * (j + 17)];
+                if (LD == PK_LD_ASYNC) {
+                    const f2* xz = xw + s;
+                    xa0 = xz[32 * jj];
+                    xa1 = xz[32 * (jj + 1)];
+                    xb0 = xz[32 * (jj + 16)];
+                    xb1 = xz[32 * (jj + 17)];
+                } else if (LD == PK_LD_DIRECT) {
+                    const f2* xz = reinterpret_cast<const f2*>(x) + s;
+                    xa0 = xz[32 * jj];
+                    xa1 = xz[32 * (jj + 1)];
+                    xb0 = xz[32 * (jj + 16)];
+                    xb1 = xz[32 * (jj + 17)];
                 } else {
-                    const cpx a0 = load_pair_guarded(x, st + 2 * (s + 32 * j), P.nsamples);
-                    const cpx a1 = load_pair_guarded(x, st + 2 * (s + 32 * (j + 1)), P.nsamples);
-                    const cpx b0 = load_pair_guarded(x, st + 2 * (s + 32 * (j + 16)), P.nsamples);
-                    const cpx b1 = load_pair_guarded(x, st + 2 * (s + 32 * (j + 17)), P.nsamples);
+                    const float* xc = x - un.st; // channel base; un.st may be negative / past the end here
+                    const cpx a0 = load_pair_guarded(xc, un.st + 2 * (s + 32 * jj), P.nsamples);
+                    const cpx a1 = load_pair_guarded(xc, un.st + 2 * (s + 32 * (jj + 1)), P.nsamples);
+                    const cpx b0 = load_pair_guarded(xc, un.st + 2 * (s + 32 * (jj + 16)), P.nsamples);
+                    const cpx b1 = load_pair_guarded(xc, un.st + 2 * (s + 32 * (jj + 17)), P.nsamples);
                     xa0 = pk(a0.x, a0.y);
                     xa1 = pk(a1.x, a1.y);
                     xb0 = pk(b0.x, b0.y);
                     xb1 = pk(b1.x, b1.y);
                 }
-                win_stage1(v, j, xa0, wa.a, xb0, wb.a);
-                win_stage1(v, j + 1, xa1, wa.b, xb1, wb.b);
+                win_stage1(v, jj, xa0, wa.a, xb0, wb.a);
+                win_stage1(v, jj + 1, xa1, wa.b, xb1, wb.b);
             }
+            if (LD == PK_LD_ASYNC) __syncwarp(); // every lane has read its samples before the transpose overwrites them
             fft32_pk_after_stage1(v);
 #pragma unroll
-            for (int k1 = 0; k1 < 32; k1 += 2) {
-                const f2x2 t = trow[k1 / 2];
-                tr_wr[k1 * 33] = (k1 == 0) ? v[0] : cmul2(v[k1], t.a);
-                tr_wr[(k1 + 1) * 33] = cmul2(v[k1 + 1], t.b);
-            }
+            for (int k1 = 0; k1 < 32; ++k1) tr_wr[k1 * Cfg::XROW] = v[k1];
             __syncwarp();
             f2 u[32];
 #pragma unroll
-            for (int jx = 0; jx < 32; ++jx) u[brev(jx, 5)] = tr_rd[jx];
-            fft32_pk(u); // u[k2] = Z[s + 32 k2]
-            __syncwarp();
-#pragma unroll
-            for (int i = 16; i < 32; ++i) ex_wr[(i - 16) * 32] = u[i];
-            ex_wr[16 * 32] = u[0];
-            __syncwarp();
-#pragma unroll
-            for (int q = 0; q < 16; ++q) {
-                const f2 zp = ex_rd[(15 - q) * 32];
-                const f2x2 wq = prow[q / 2];
-                const f2 A = add2(u[q], conj2(zp));  // Z[k] + conj Z[M-k]
-                const f2 Bv = sub2(u[q], conj2(zp)); // Z[k] - conj Z[M-k]
-                const f2 T = cmul2(Bv, (q & 1) ? wq.b : wq.a);
-                const f2 xp = add2(A, T), xm = sub2(A, T);
-                alo[q] = fm(lo(xp), lo(xp), fm(hi(xp), hi(xp), alo[q]));
-                ahi[q] = fm(lo(xm), lo(xm), fm(hi(xm), hi(xm), ahi[q]));
+            for (int jx = 0; jx < 32; jx += 2) {
+                const f2x2 t = tr_rd[jx / 2];
+                u[brev(jx, 5)] = t.a;
+                u[brev(jx + 1, 5)] = t.b;
             }
-            { // bin 512 (lane 0, self-paired): X = 2 conj Z
-                const float a = lo(u[16]), b = hi(u[16]);
+            __syncwarp(); // the buffer is free again
+            if (LD == PK_LD_ASYNC) {
+                // start the copy of what this warp transforms next: the next channel of this frame, or the first
+                // channel of its next frame
+                if (!last) {
+                    pk_prefetch(xw, x + P.channel_stride, s, bar);
+                } else if (g + gstep < total) {
+                    const PkUnit nx = pk_unit(P, g + gstep);
+                    pk_prefetch(xw, P.samples + nx.stream * P.stream_stride + ch0 * P.channel_stride + nx.st, s, bar);
+                }
+            }
+            fft32_twisted(u, trow); // u[k2] = Z[s + 32 k2]
+            // Real-FFT split per pair (k, M-k), k = s + 32 q.  Z[M-k] is register 31 - q of lane 32 - s; lane 0 pairs with
+            // its own register 32 - q.  The last channel goes straight on to dB / colour / store.
+            if (!last) {
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    const f2 zp = sel2(s == 0, u[(32 - q) & 31], shfl2(u[31 - q], partner));
+                    const f2x2 wq = prow[q / 2];
+                    const f2 A = add2(u[q], conj2(zp));  // Z[k] + conj Z[M-k]
+                    const f2 Bv = sub2(u[q], conj2(zp)); // Z[k] - conj Z[M-k]
+                    const f2 T = cmul2(Bv, (q & 1) ? wq.b : wq.a);
+                    const f2 xp = add2(A, T), xm = sub2(A, T);
+                    alo[q] = fm(lo(xp), lo(xp), fm(hi(xp), hi(xp), alo[q]));
+                    ahi[q] = fm(lo(xm), lo(xm), fm(hi(xm), hi(xm), ahi[q]));
+                }
+                const float a = lo(u[16]), b = hi(u[16]); // bin 512 (lane 0, self-paired): X = 2 conj Z
                 amid = fm(JADE_FMUL(4.0f, a), a, fm(JADE_FMUL(4.0f, b), b, amid));
-            }
-            __syncwarp();
-        }
-
-        const ColOut o = col_out(P, stream, j);
-        // reference orientation: bin k lands in row M - k.  lane s: bins s+32q -> rows M-s-32q ; bins M-s-32q -> rows s+32q
-        uint32_t* p_lo = o.pix ? o.pix + (M - s) : nullptr;
-        uint32_t* p_hi = o.pix ? o.pix + s : nullptr;
-        float* d_lo = (WANT_DB && o.db) ? o.db + s : nullptr;
-        float* d_hi = (WANT_DB && o.db) ? o.db + (M - s) : nullptr;
+            } else {
+                uint32_t* p_lo = o.pix ? o.pix + (M - s) : nullptr;
+                uint32_t* p_hi = o.pix ? o.pix + s : nullptr;
+                float* d_lo = (WANT_DB && o.db) ? o.db + s : nullptr;
+                float* d_hi = (WANT_DB && o.db) ? o.db + (M - s) : nullptr;
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-            const float dl = to_db_fast(MIXK == MIX_SUM ? JADE_FMUL(alo[q], scale) : alo[q]);
-            const float dh = to_db_fast(MIXK == MIX_SUM ? JADE_FMUL(ahi[q], scale) : ahi[q]);
-            if (WANT_DB && d_lo) {
-                d_lo[32 * q] = dl;
-                d_hi[-32 * q] = dh;
+                for (int q = 0; q < 16; ++q) {
+                    const f2 zp = sel2(s == 0, u[(32 - q) & 31], shfl2(u[31 - q], partner));
+                    const f2x2 wq = prow[q / 2];
+                    const f2 A = add2(u[q], conj2(zp));
+                    const f2 Bv = sub2(u[q], conj2(zp));
+                    const f2 T = cmul2(Bv, (q & 1) ? wq.b : wq.a);
+                    const f2 xp = add2(A, T), xm = sub2(A, T);
+                    const float pl = fm(lo(xp), lo(xp), fm(hi(xp), hi(xp), MIXK == MIX_NONE ? 0.f : alo[q]));
+                    const float ph = fm(lo(xm), lo(xm), fm(hi(xm), hi(xm), MIXK == MIX_NONE ? 0.f : ahi[q]));
+                    emit(pl, p_lo ? p_lo - 32 * q : nullptr, d_lo ? d_lo + 32 * q : nullptr);
+                    emit(ph, p_hi ? p_hi + 32 * q : nullptr, d_hi ? d_hi - 32 * q : nullptr);
+                }
+                if (s == 0) {
+                    const float a = lo(u[16]), b = hi(u[16]);
+                    const float pm = fm(JADE_FMUL(4.0f, a), a, fm(JADE_FMUL(4.0f, b), b, MIXK == MIX_NONE ? 0.f : amid));
+                    emit(pm, o.pix ? o.pix + 512 : nullptr, (WANT_DB && o.db) ? o.db + 512 : nullptr);
+                }
             }
-            if (p_lo) {
-                p_lo[-32 * q] = colour_of(dl, P, s_pal);
-                p_hi[32 * q] = colour_of(dh, P, s_pal);
-            }
-        }
-        if (s == 0) {
-            const float dm = to_db_fast(MIXK == MIX_SUM ? JADE_FMUL(amid, scale) : amid);
-            if (WANT_DB && o.db) o.db[512] = dm;
-            if (o.pix) o.pix[512] = colour_of(dm, P, s_pal);
         }
     }
 }

@@ -23,6 +23,7 @@ struct BlockState {
     std::vector<pthread_barrier_t> warp_bar;
     std::vector<char> smem;
     std::vector<float> mail; // one slot per thread: warp shuffles
+    std::vector<unsigned long long> mail64;
 };
 inline thread_local dim3 t_threadIdx, t_blockIdx;
 inline dim3 g_blockDim, g_gridDim;
@@ -47,6 +48,16 @@ inline float __shfl_xor_sync(unsigned, float v, int lane_mask)
     __syncwarp();
     return r;
 }
+inline unsigned long long __shfl_sync(unsigned, unsigned long long v, int src_lane)
+{
+    jade_emu::BlockState& st = *jade_emu::g_block;
+    const unsigned tid = threadIdx.x;
+    st.mail64[tid] = v;
+    __syncwarp();
+    const unsigned long long r = st.mail64[(tid & ~31u) | ((unsigned)src_lane & 31u)];
+    __syncwarp();
+    return r;
+}
 inline int max(int a, int b) { return a > b ? a : b; }
 inline int min(int a, int b) { return a < b ? a : b; }
 inline float sinpif(float x) { return (float)std::sin(M_PI * (double)x); }
@@ -62,6 +73,7 @@ void launch(K kernel, unsigned grid, unsigned block, size_t smem_bytes, A... arg
         BlockState st;
         st.smem.assign(smem_bytes + 64, 0);
         st.mail.assign(block, 0.f);
+        st.mail64.assign(block, 0ull);
         pthread_barrier_init(&st.block_bar, nullptr, block);
         const unsigned nw = (block + 31) / 32;
         st.warp_bar.resize(nw);

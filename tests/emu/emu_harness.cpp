@@ -44,8 +44,13 @@ void run_cta(const KParams& P, int mixk, bool general, int grid)
 template <int T, int MIXK, bool WDB, bool GUARD>
 void run_pk_one(const KParams& P, int npal, int grid)
 {
-    const int block = jade::PkCfg::WARPS * 32;
-    if constexpr (T == 32) jade_emu::launch(jade::stft_pk2048_kernel<MIXK, WDB, GUARD>, grid, block, jade::PkCfg::smem_bytes(npal), P);
+    const int block = (T == 32 ? jade::PkCfg::WARPS : jade::PkSmallCfg<2>::WARPS) * 32;
+    if constexpr (T == 32) {
+        // same routing as launch_stft: guard / cp.async staging (16-byte aligned) / LDG to registers (8-byte aligned)
+        if (GUARD) jade_emu::launch(jade::stft_pk2048_kernel<MIXK, WDB, jade::PK_LD_GUARD>, grid, block, jade::PkCfg::smem_bytes(npal), P);
+        else if (P.aligned4) jade_emu::launch(jade::stft_pk2048_kernel<MIXK, WDB, jade::PK_LD_ASYNC>, grid, block, jade::PkCfg::smem_bytes(npal), P);
+        else jade_emu::launch(jade::stft_pk2048_kernel<MIXK, WDB, jade::PK_LD_DIRECT>, grid, block, jade::PkCfg::smem_bytes(npal), P);
+    }
     else jade_emu::launch(jade::stft_pksmall_kernel<T, MIXK, WDB, GUARD>, grid, block, jade::PkSmallCfg<T>::smem_bytes(npal), P);
 }
 template <int T>
@@ -125,6 +130,8 @@ extern "C" int emu_render(const jade_config* cin, const int32_t* palette, int np
     P.nsamples = nsamples;
     P.sample_base = 0;
     P.aligned2 = ((nsamples % 2) == 0 && (c.hop % 2) == 0 && (c.block_stride % 2) == 0 && (c.preroll % 2) == 0) ? 1 : 0;
+    P.aligned4 = ((nsamples % 4) == 0 && (c.hop % 4) == 0 && (c.block_stride % 4) == 0 && (c.preroll % 4) == 0 &&
+                  ((uintptr_t)samples % 16) == 0) ? 1 : 0;
     P.N = N; P.M = M; P.B = B;
     P.hop = c.hop; P.fb = c.frames_per_block; P.bstride = c.block_stride; P.preroll = c.preroll;
     P.first_col = first_col; P.ncols = ncols; P.nstreams = nstreams;

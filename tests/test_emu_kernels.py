@@ -44,6 +44,22 @@ def test_emulated_kernels_match_oracle(N, hop, ch, window, mix):
         parity.check_pixels(pix[s], opix, odb[:, ::-1], -50.0, 50.0, 256, f"stream {s}")
 
 
+@pytest.mark.parametrize("extra,want_db", [(0, True), (0, False), (2, True), (1, True)])
+def test_emulated_pk2048_prefetch_chain(extra, want_db):
+    """N = 2048 with several frames per warp: the cp.async staging of the next channel / next frame (16-byte aligned
+    input, extra = 0), the LDG-to-register instantiation (8-byte aligned only, extra = 2) and the guarded one (odd
+    length, extra = 1) must give the same columns as the oracle, for both the pixel-only and the dB-storing forms."""
+    N, hop, ch, ncols = 2048, 512, 2, 30
+    x = signals.streams(2, ch, hop * (ncols - 1) + 64 + extra, 48000.0)
+    pal = O.Palette(256, O.PAL["jade"]).table()
+    db, pix = E.render(_cfg(N, hop, ch, "hann", "absmean"), pal, -50.0, 50.0, x, 0, ncols, N // 2 + 1, grid=1, want_db=want_db)
+    for s in range(x.shape[0]):
+        odb, opix = O.render_batch(x[s], fft_size=N, hop=hop, window="hann", mix="absmean", ncols=ncols)
+        if want_db:
+            parity.check_db(db[s], odb, N, f"stream {s}")
+        parity.check_pixels(pix[s], opix, odb[:, ::-1], -50.0, 50.0, 256, f"stream {s}")
+
+
 def test_emulated_general_epilogue_options():
     N, hop = 1024, 256
     x = signals.streams(1, 2, hop * 8, 48000.0)
