@@ -345,6 +345,7 @@ void fill_params(jade_engine* e, KParams& P)
     P.pmax = e->range.mx;
     P.pmaxc = e->range.maxclamp();
     P.pmult = e->range.mult;
+    jade::colour_fold(P);
     P.db_precise = c.db_precise;
     P.pooled = e->pooled ? 1 : 0;
     P.R = e->R;

@@ -86,6 +86,10 @@ struct KParams {
     const uint32_t* palette; // npal entries, alpha / byte order already baked in
     int npal;
     float pmin, pmax, pmaxc, pmult; // CColorPalette m_Min, m_Max, m_Max*0.9999f, m_AccessMult
+    // the same lookup folded onto lg = log2(p + 1e-11) (colour_of_lg, N = 2048 kernel): index = trunc(lg*ck1 + ck0),
+    // lg >= clg_hi (dB >= m_Max) gives ci_hi = index of m_Max*0.9999
+    float ck1, ck0, clg_hi;
+    int ci_hi;
     int db_precise;         // 1: float(10.0*log10(double(p+1e-11f))) exactly as the reference; 0: MUFU log2
     // ---- rows
     int pooled;             // 0: rows are bins [k_lo,k_hi); 1: row r = max over bins [row_bins[r].lo, row_bins[r].hi)
@@ -131,6 +135,26 @@ JADE_DEVICE uint32_t colour_of(float v, const KParams& P, const uint32_t* pal)
     int idx = (int)JADE_FMUL(d, P.pmult);
     idx = max(min(idx, P.npal - 1), 0);
     return pal[idx];
+}
+
+// The same lookup from lg = log2(p + 1e-11) with the dB scale folded in: one FFMA instead of FMUL, FADD, FMUL, and the lower
+// clamp left to the integer RELU.  The index can differ from colour_of(3.0103 lg) only where the dB value lies within
+// ~1e-5 dB of an index edge (the parity tolerance is 1e-3 dB, tests/parity.py).
+JADE_DEVICE uint32_t colour_of_lg(float lg, const KParams& P, const uint32_t* pal)
+{
+    int idx = (int)fm(lg, P.ck1, P.ck0);
+    idx = max(min(idx, P.npal - 1), 0);
+    idx = (lg >= P.clg_hi) ? P.ci_hi : idx;
+    return pal[idx];
+}
+// host side: fill ck1, ck0, clg_hi, ci_hi from pmin, pmax, pmaxc, pmult, npal
+inline void colour_fold(KParams& P)
+{
+    P.ck1 = 3.01029995663981195f * P.pmult;
+    P.ck0 = -P.pmin * P.pmult;
+    P.clg_hi = P.pmax / 3.01029995663981195f;
+    int ih = (int)((P.pmaxc > P.pmin ? P.pmaxc - P.pmin : 0.0f) * P.pmult);
+    P.ci_hi = ih < 0 ? 0 : (ih > P.npal - 1 ? P.npal - 1 : ih);
 }
 
 JADE_DEVICE cpx load_pair_guarded(const float* JADE_RESTRICT x, long long idx, long long ns)

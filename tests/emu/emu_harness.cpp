@@ -140,6 +140,7 @@ extern "C" int emu_render(const jade_config* cin, const int32_t* palette, int np
     P.twP = reinterpret_cast<const jade::cpx*>(twP.data());
     P.palette = baked.data(); P.npal = npal;
     P.pmin = range.mn; P.pmax = range.mx; P.pmaxc = range.maxclamp(); P.pmult = range.mult;
+    jade::colour_fold(P);
     P.db_precise = c.db_precise;
     P.pooled = pooled; P.R = R; P.k_lo = k_lo; P.k_hi = k_hi; P.flip = c.flip_y;
     P.row_bins = rb.data();
