@@ -1,20 +1,30 @@
 // jade_pk.cuh -- the headline kernel: N = 2048 (BASELINE configs[1] / [3]) with packed FP32x2 arithmetic.
 //
 // Same fused path as jade_kernels.cuh (framing, window, real FFT, |X|^2, channel mix, dB, flip, palette, packed pixel
-// store; reference lines cited there), restructured around what limits it on sm_100a:
+// store; reference lines cited there), restructured around what limits it on sm_100a (profiles/r01*, r02*):
 //   * every complex value lives in ONE 64-bit register pair and all butterflies / twiddle products are FFMA2 / FADD2 /
 //     FMUL2 (PTX fma/add/mul.rn.f32x2): a complex add is 1 instruction, a complex multiply 2, a general radix-2
 //     butterfly 3 (a' = a + W b by two chained FFMA2, b' = 2a - a').  ptxas folds the half-swap, the per-half sign
 //     and the scalar broadcast into operand modifiers (R.F32x2.LO_HI.NP, R.F32), so no repacking moves are needed.
-//     This halves the issue slots of the FP32 work, which was the measured limiter (profiles/r01b: issue-active 64 %).
+//   * a warp never waits for global memory: while it runs pass 2, the split and the epilogue of one channel, the TMA
+//     engine (cp.async.bulk, one instruction of lane 0, completion on a per-warp mbarrier) copies the 8 KB of the NEXT
+//     channel / frame into the warp's own shared-memory buffer -- the same buffer the transpose went through a moment
+//     before.  No registers are tied up by loads in flight.
+//   * the inter-pass twiddles are folded into the pass-2 butterflies ("twisted" DIT, see fft32_twisted): 16 table values
+//     per lane instead of 31 and no separate twiddle multiply.
 //   * the real-FFT split is done per PAIR (k, M-k): A = Z[k]+conj Z[M-k], B = Z[k]-conj Z[M-k], T = (-i W_N^k) B,
-//     X[k] = A+T, X[M-k] = conj(A-T): 8 FP32 instructions per bin instead of 13, and only the upper half of the
-//     spectrum crosses lanes (17 shared-memory words per lane instead of 33+32).
-//   * per-lane tables (window, inter-pass twiddles, split twiddles) are laid out [lane][index] with a 16-byte row pad, so
-//     that they are read with conflict-free LDS.128 (two table entries per instruction).
+//     X[k] = A+T, X[M-k] = conj(A-T): 8 FP32 instructions per bin instead of 13.  Z[M-k] sits in lane 32 - s, register
+//     31 - q and arrives by SHFL.IDX; nothing goes through shared memory for it.
+//   * the last channel's split loop goes straight on to dB, palette index (one FFMA from the log2, colour_of_lg) and the
+//     coalesced pixel store, so accumulators die as they are consumed and the epilogue overlaps FP work.
+//   * per-lane tables (window, twisted twiddles, split twiddles) are laid out [lane][index] with a 16-byte row pad, so
+//     that they are read with conflict-free LDS.128 (two table entries per instruction); the transpose rows are 16-byte
+//     aligned for the same reason.
+//   * 12 warps per SM with up to 168 registers each (one CTA per SM): the 16-warp / 128-register shape spills the stereo
+//     accumulators and is 12 % slower; 8 warps lose 8 % (profiles/r02_pk2048_variants.txt).
 //
 // One warp transforms one frame: M = 1024 complex points z[m] = x[2m] + i x[2m+1], 32 per lane (m = s + 32 n1), radix-32
-// in registers, one padded transpose through shared memory, radix-32 in registers: lane s ends with Z[s + 32 k2].
+// in registers, one transpose through shared memory, twisted radix-32 in registers: lane s ends with Z[s + 32 k2].
 #pragma once
 #include "jade_kernels.cuh"
 
