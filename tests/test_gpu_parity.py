@@ -30,6 +30,8 @@ CASES = [
     (8192, 2048, 1, "hann", "max"),
     (32768, 8192, 1, "hann", "absmean"),
     (2048, 512, 1, "hann", "min"),            # Min with one channel clamps at 1e6
+    (2048, 510, 2, "hann", "absmean"),        # frames 8- but not 16-byte aligned: the LDG instantiation of the N=2048 kernel
+    (2048, 205, 2, "hann", "absmean"),        # odd hop: every column through the guarded instantiation
 ]
 
 
