@@ -157,6 +157,21 @@ inline void colour_fold(KParams& P)
     P.ci_hi = ih < 0 ? 0 : (ih > P.npal - 1 ? P.npal - 1 : ih);
 }
 
+// Fast-path epilogue of one bin (packed kernels): mixed power -> lg = log2(p' + 1e-11) -> dB value (optional) and pixel.
+// MIX_SUM is only routed here for 2^n channels, so the single FFMA rounds exactly like (p * scale) + 1e-11; dB = 3.0103 lg
+// is to_db_fast.  pix / db may be null when WANT_DB (the plain instantiations are only launched with a pixel buffer).
+template <int MIXK, bool WANT_DB>
+JADE_DEVICE void emit_bin(float p, float scale, uint32_t* pix, float* db, const KParams& P, const uint32_t* pal)
+{
+    const float lg = JADE_LOG2F(MIXK == 1 /* MIX_SUM */ ? fm(p, scale, 1e-11f) : JADE_FADD(p, 1e-11f));
+    if (WANT_DB) {
+        if (db) *db = JADE_FMUL(3.01029995663981195f, lg);
+        if (pix) *pix = colour_of_lg(lg, P, pal);
+    } else {
+        *pix = colour_of_lg(lg, P, pal);
+    }
+}
+
 JADE_DEVICE cpx load_pair_guarded(const float* JADE_RESTRICT x, long long idx, long long ns)
 {
     cpx r;

@@ -471,18 +471,9 @@ JADE_KERNEL(PkCfg::WARPS * 32, JADE_PK_CTAS) stft_pk2048_kernel(const KParams P)
     if (MIXK == MIX_NONE) ch1 = ch0 + 1;
     const float scale = (MIXK == MIX_SUM) ? (1.0f / (float)P.channels) : 1.0f;
 
-    // One column: dB, palette, packed pixel (and the dB value for the streaming ring).  Reference orientation: bin k lands
+    // One bin: dB, palette, packed pixel (and the dB value for the streaming ring).  Reference orientation: bin k lands
     // in row M - k, so lane s writes rows M-s-32q (bins s+32q) and rows s+32q (bins M-s-32q): both coalesced.
-    auto emit = [&](float p, uint32_t* pix, float* db) {
-        // dB = 3.0103 lg as in to_db_fast; scale = 2^-n, so the single FFMA rounds exactly like (p * scale) + 1e-11
-        const float lg = JADE_LOG2F(MIXK == MIX_SUM ? fm(p, scale, 1e-11f) : JADE_FADD(p, 1e-11f));
-        if (WANT_DB) {
-            if (db) *db = JADE_FMUL(3.01029995663981195f, lg);
-            if (pix) *pix = colour_of_lg(lg, P, s_pal);
-        } else {
-            *pix = colour_of_lg(lg, P, s_pal); // the plain instantiation is only launched with a pixel buffer
-        }
-    };
+    auto emit = [&](float p, uint32_t* pix, float* db) { emit_bin<MIXK, WANT_DB>(p, scale, pix, db, P, s_pal); };
 
     unsigned g = blockIdx.x * Cfg::WARPS + warp;
     if (LD == PK_LD_ASYNC && g < total) {

@@ -189,22 +189,10 @@ JADE_KERNEL(32 * R1, PkCtaCfg<R1>::MINB) stft_pkcta_kernel(const KParams P)
         float* d_hi = (WANT_DB && o.db) ? o.db + (M - t) : nullptr;
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
-            const float dl = to_db_fast(MIXK == MIX_SUM ? JADE_FMUL(alo[q], scale) : alo[q]);
-            const float dh = to_db_fast(MIXK == MIX_SUM ? JADE_FMUL(ahi[q], scale) : ahi[q]);
-            if (WANT_DB && d_lo) {
-                d_lo[THREADS * q] = dl;
-                d_hi[-THREADS * q] = dh;
-            }
-            if (p_lo) {
-                p_lo[-THREADS * q] = colour_of(dl, P, s_pal);
-                p_hi[THREADS * q] = colour_of(dh, P, s_pal);
-            }
+            emit_bin<MIXK, WANT_DB>(alo[q], scale, (!WANT_DB || p_lo) ? p_lo - THREADS * q : nullptr, d_lo ? d_lo + THREADS * q : nullptr, P, s_pal);
+            emit_bin<MIXK, WANT_DB>(ahi[q], scale, (!WANT_DB || p_hi) ? p_hi + THREADS * q : nullptr, d_hi ? d_hi - THREADS * q : nullptr, P, s_pal);
         }
-        if (t == 0) {
-            const float dm = to_db_fast(MIXK == MIX_SUM ? JADE_FMUL(amid, scale) : amid);
-            if (WANT_DB && o.db) o.db[M / 2] = dm;
-            if (o.pix) o.pix[M / 2] = colour_of(dm, P, s_pal);
-        }
+        if (t == 0) emit_bin<MIXK, WANT_DB>(amid, scale, (!WANT_DB || o.pix) ? o.pix + M / 2 : nullptr, (WANT_DB && o.db) ? o.db + M / 2 : nullptr, P, s_pal);
     }
 }
 

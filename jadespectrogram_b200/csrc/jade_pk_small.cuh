@@ -175,6 +175,7 @@ JADE_KERNEL(PkSmallCfg<T>::WARPS * 32, 2) stft_pksmall_kernel(const KParams P)
 
         const ColOut o = active ? col_out(P, stream, j) : ColOut{nullptr, nullptr};
         // reference orientation: bin k lands in row M - k
+        if (!WANT_DB && !o.pix) continue; // padding lane group of the last column group: nothing to store
         uint32_t* p_lo = o.pix ? o.pix + (M - s) : nullptr; // bin k(q)   -> row M - k(q)
         uint32_t* p_hi = o.pix ? o.pix + s : nullptr;       // bin M-k(q) -> row k(q)
         float* d_lo = (WANT_DB && o.db) ? o.db + s : nullptr;
@@ -182,22 +183,10 @@ JADE_KERNEL(PkSmallCfg<T>::WARPS * 32, 2) stft_pksmall_kernel(const KParams P)
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
             const int koff = T * (q / H) + 32 * (q % H); // k(q) - s
-            const float dl = to_db_fast(MIXK == MIX_SUM ? JADE_FMUL(alo[q], scale) : alo[q]);
-            const float dh = to_db_fast(MIXK == MIX_SUM ? JADE_FMUL(ahi[q], scale) : ahi[q]);
-            if (WANT_DB && d_lo) {
-                d_lo[koff] = dl;
-                d_hi[-koff] = dh;
-            }
-            if (p_lo) {
-                p_lo[-koff] = colour_of(dl, P, s_pal);
-                p_hi[koff] = colour_of(dh, P, s_pal);
-            }
+            emit_bin<MIXK, WANT_DB>(alo[q], scale, (!WANT_DB || p_lo) ? p_lo - koff : nullptr, d_lo ? d_lo + koff : nullptr, P, s_pal);
+            emit_bin<MIXK, WANT_DB>(ahi[q], scale, (!WANT_DB || p_hi) ? p_hi + koff : nullptr, d_hi ? d_hi - koff : nullptr, P, s_pal);
         }
-        if (s == 0) {
-            const float dm = to_db_fast(MIXK == MIX_SUM ? JADE_FMUL(amid, scale) : amid);
-            if (WANT_DB && o.db) o.db[M / 2] = dm;
-            if (o.pix) o.pix[M / 2] = colour_of(dm, P, s_pal);
-        }
+        if (s == 0) emit_bin<MIXK, WANT_DB>(amid, scale, (!WANT_DB || o.pix) ? o.pix + M / 2 : nullptr, (WANT_DB && o.db) ? o.db + M / 2 : nullptr, P, s_pal);
     }
 }
 
