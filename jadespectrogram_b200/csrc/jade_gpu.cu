@@ -55,6 +55,7 @@ kernel_fn cta_kernel(int R1, int mixk, bool general);             // jade_k_cta.
 kernel_fn pkcta_kernel(int R1, int mixk, bool want_db);           // jade_k_pkcta.cu
 kernel_fn pkcta2_kernel(int mixk);                                // jade_k_pkcta.cu
 kernel_fn pk2048_kernel(int mixk, bool want_db, int load);        // jade_k_pk.cu (load = jade::PK_LD_*)
+kernel_fn pk2048x2_kernel(bool want_db);                           // jade_k_pk2.cu (stereo: both channels per warp)
 kernel_fn pksmall_kernel(int T, int mixk, bool want_db, bool guard); // jade_k_pksmall_a.cu / _b.cu
 } // namespace jade_k
 namespace {
@@ -124,6 +125,8 @@ struct jade_engine {
     KernelChoice kc_edge;  // family 3 only: guarded-load instantiation for boundary columns / unaligned geometries
     KernelChoice kc_mid;   // N = 2048 only: LDG-to-register instantiation for 8- but not 16-byte aligned frames
     bool has_mid = false;
+    KernelChoice kc_pair;  // N = 2048, AbsMean over exactly two channels: both channels of a frame per warp
+    bool has_pair = false;
     int mixk = 0;          // jade::MIX_NONE / MIX_SUM / MIX_SEL
     bool general = false;  // general (rolled) epilogue: pooled / cropped rows, precise dB, non-2^n channel mean, Max/Min
     bool pooled = false;
@@ -227,6 +230,26 @@ int choose_kernel(jade_engine* e)
             km.blocks_per_sm = occ_m;
             e->kc_mid = km;
             e->has_mid = true;
+            // stereo kernel: the two channels of a frame share every table read
+            e->has_pair = false;
+            const int contributing = (e->cfg.mix_mode == JADE_MIX_LEFT || e->cfg.mix_mode == JADE_MIX_RIGHT) ? 1 : e->cfg.channels;
+            if (mu == jade::MIX_SUM && contributing == 2) {
+                KernelChoice kp = kc;
+                snprintf(kp.name, sizeof kp.name, "pk2048x2");
+                kp.threads = jade::PkPairCfg::WARPS * 32;
+                kp.units_per_block = jade::PkPairCfg::WARPS;
+                kp.smem = jade::PkPairCfg::smem_bytes(e->npal);
+                kp.fn = jade_k::pk2048x2_kernel(false);
+                kp.fn_db = jade_k::pk2048x2_kernel(true);
+                CU(e, cudaFuncSetAttribute((const void*)kp.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.smem));
+                CU(e, cudaFuncSetAttribute((const void*)kp.fn_db, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.smem));
+                int occ_p = 0;
+                CU(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_p, (const void*)kp.fn, kp.threads, kp.smem));
+                if (occ_p < 1) return fail(e, JADE_ERR_CUDA, "kernel %s does not fit on an SM (smem %d)", kp.name, kp.smem);
+                kp.blocks_per_sm = occ_p;
+                e->kc_pair = kp;
+                e->has_pair = true;
+            }
         }
         ke.fn_db = nullptr;
         CU(e, cudaFuncSetAttribute((const void*)kc.fn_db, cudaFuncAttributeMaxDynamicSharedMemorySize, kc.smem));
@@ -407,7 +430,8 @@ int launch_stft(jade_engine* e, KParams& P, cudaStream_t st)
     // to the guarded-load instantiation
     if (!P.aligned2) return launch_one(e, e->kc_edge, P, st);
     static const bool force_ldg = [] { const char* v = getenv("JADE_PK_LOAD"); return v && !strcmp(v, "ldg"); }(); // experiments
-    const KernelChoice& main_kc = (e->has_mid && (!P.aligned4 || force_ldg)) ? e->kc_mid : e->kc;
+    static const bool no_pair = [] { const char* v = getenv("JADE_PK_LOAD"); return v && !strcmp(v, "single"); }();
+    const KernelChoice& main_kc = (e->has_mid && (!P.aligned4 || force_ldg)) ? e->kc_mid : ((e->has_pair && !no_pair) ? e->kc_pair : e->kc);
     const long long j0 = P.first_col, j1 = P.first_col + P.ncols;
     auto start = [&](long long j) { return frame_start_abs(e->cfg, j) - P.sample_base; };
     long long lo = j0, hi = j1;

@@ -219,6 +219,11 @@ __device__ __forceinline__ f2 sel2(bool c, f2 a, f2 b) { return c ? a : b; }
 #if defined(JADE_EMU)
 inline void mbar_init(unsigned long long*, int) {}
 inline void bulk_copy_g2s(void* dst, const void* src, int bytes, unsigned long long*) { std::memcpy(dst, src, (size_t)bytes); }
+inline void bulk_copy2_g2s(void* dst0, const void* src0, void* dst1, const void* src1, int bytes, unsigned long long*)
+{
+    std::memcpy(dst0, src0, (size_t)bytes);
+    std::memcpy(dst1, src1, (size_t)bytes);
+}
 inline void mbar_wait(unsigned long long*, unsigned) {}
 #else
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, int count)
@@ -234,6 +239,21 @@ __device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, int by
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d), "l"(src),
+                 "r"(bytes), "r"(b)
+                 : "memory");
+}
+// two copies of `bytes` each, one completion (2 * bytes) on the barrier
+__device__ __forceinline__ void bulk_copy2_g2s(void* dst0, const void* src0, void* dst1, const void* src1, int bytes,
+                                               unsigned long long* bar)
+{
+    const unsigned d0 = (unsigned)__cvta_generic_to_shared(dst0), d1 = (unsigned)__cvta_generic_to_shared(dst1);
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(2 * bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d0), "l"(src0),
+                 "r"(bytes), "r"(b)
+                 : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d1), "l"(src1),
                  "r"(bytes), "r"(b)
                  : "memory");
 }
@@ -338,6 +358,44 @@ JADE_DEVICE void fft32_twisted(f2* u, const f2x2* trow)
     // LEN 32 in two halves (entries J = 0..3, then 4..7; J + 8 is -i times entry J) so that only four twiddles are live
     tw32_half<0>(u, trow[4], trow[5]);
     tw32_half<4>(u, trow[6], trow[7]);
+}
+
+// two transforms at once: every table value is read once and used for both
+template <int J0>
+JADE_DEVICE void tw32_half2(f2* ua, f2* ub, const f2x2 ta, const f2x2 tb)
+{
+    const f2 w[4] = {ta.a, ta.b, tb.a, tb.b};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        bfly_w(ua[J0 + i], ua[J0 + i + 16], w[i]);
+        bfly_w(ub[J0 + i], ub[J0 + i + 16], w[i]);
+        bfly_wmi(ua[J0 + i + 8], ua[J0 + i + 24], w[i]);
+        bfly_wmi(ub[J0 + i + 8], ub[J0 + i + 24], w[i]);
+    }
+}
+JADE_DEVICE void fft32_twisted2(f2* ua, f2* ub, const f2x2* trow)
+{
+    {
+        const f2x2 t = trow[0];
+        tw_blocks<2, 0>(ua, &t.a);
+        tw_blocks<2, 0>(ub, &t.a);
+        tw_blocks<4, 0>(ua, &t.b);
+        tw_blocks<4, 0>(ub, &t.b);
+    }
+    {
+        const f2x2 t = trow[1];
+        const f2 w[2] = {t.a, t.b};
+        tw_blocks<8, 0>(ua, w);
+        tw_blocks<8, 0>(ub, w);
+    }
+    {
+        const f2x2 t0 = trow[2], t1 = trow[3];
+        const f2 w[4] = {t0.a, t0.b, t1.a, t1.b};
+        tw_blocks<16, 0>(ua, w);
+        tw_blocks<16, 0>(ub, w);
+    }
+    tw32_half2<0>(ua, ub, trow[4], trow[5]);
+    tw32_half2<4>(ua, ub, trow[6], trow[7]);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -590,6 +648,150 @@ JADE_KERNEL(PkCfg::WARPS * 32, JADE_PK_CTAS) stft_pk2048_kernel(const KParams P)
                     emit(pm, o.pix ? o.pix + 512 : nullptr, (WANT_DB && o.db) ? o.db + 512 : nullptr);
                 }
             }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Stereo kernel (AbsMean over exactly two channels, the BASELINE configs[1] shape): one warp transforms BOTH channels of a
+// frame at once, so that every window, twiddle and split-twiddle value is read from shared memory once for the two
+// (the shared-memory pipe is the limiter, profiles/r02_pk2048_stereo.txt: the tables are 256 of 813 wavefronts per stereo
+// frame), the two powers add up without accumulators living through a transform, and the two independent dependency
+// chains give the scheduler extra parallelism.  12 warps per SM, <= 168 registers.  Interior, 16-byte aligned frames only
+// (TMA staging as in PK_LD_ASYNC, one mbarrier completion for the two 8 KB copies); everything else goes to
+// stft_pk2048_kernel, whose per-channel arithmetic is the same code in the same order, so the results are bit-identical.
+// (The same pairing applied to two consecutive mono columns is slower than one transform per warp: 433 M vs 485 M
+// frames/s, gpurun_out/variants10.txt -- mono keeps stft_pk2048_kernel.)
+// ---------------------------------------------------------------------------------------------------------
+struct PkPairCfg {
+    static constexpr int WARPS = 12;
+    static JADE_HD int off_bar(int npal) { return PkCfg::off_pal + (npal * 4 + 15) / 16 * 16; }
+    static JADE_HD int off_xch(int npal) { return off_bar(npal) + (WARPS * 8 + 15) / 16 * 16; }
+    static JADE_HD int smem_bytes(int npal) { return off_xch(npal) + WARPS * 2 * PkCfg::XCH * 8; }
+};
+
+template <bool WANT_DB>
+JADE_KERNEL(PkPairCfg::WARPS * 32, 1) stft_pk2048x2_kernel(const KParams P)
+{
+    using Cfg = PkCfg;
+    constexpr int M = Cfg::M, WARPS = PkPairCfg::WARPS, XCH = Cfg::XCH;
+    JADE_DYN_SMEM(smem);
+    char* sm = reinterpret_cast<char*>(smem);
+    f2* s_win = reinterpret_cast<f2*>(sm + Cfg::off_win);
+    f2* s_tw2 = reinterpret_cast<f2*>(sm + Cfg::off_tw2);
+    f2* s_twP = reinterpret_cast<f2*>(sm + Cfg::off_twP);
+    uint32_t* s_pal = reinterpret_cast<uint32_t*>(sm + Cfg::off_pal);
+    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(sm + PkPairCfg::off_bar(P.npal));
+    f2* s_xch = reinterpret_cast<f2*>(sm + PkPairCfg::off_xch(P.npal));
+
+    for (int i = threadIdx.x; i < M; i += blockDim.x) {
+        const int s = i & 31, n1 = i >> 5;
+        s_win[s * Cfg::ROW + n1] = pk(P.window[2 * i], P.window[2 * i + 1]);
+    }
+    if (threadIdx.x < WARPS) mbar_init(s_bar + threadIdx.x, 1);
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) {
+        const int s = i & 31, q = i >> 5;
+        const cpx t = P.twP[2 * tw2_exponent(s, q)];
+        s_tw2[s * Cfg::TROW + q] = pk(t.x, t.y);
+        const cpx w = P.twP[s + 32 * q];
+        s_twP[s * Cfg::PROW + q] = pk(w.y, -w.x);
+    }
+    for (int i = threadIdx.x; i < P.npal; i += blockDim.x) s_pal[i] = P.palette[i];
+    __syncthreads();
+
+    const int s = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    f2* xa = s_xch + warp * 2 * XCH; // buffer of channel 0
+    f2* xb = xa + XCH;               //           channel 1
+    unsigned long long* bar = s_bar + warp;
+    unsigned copies = 0;
+    const f2x2* wrow = reinterpret_cast<const f2x2*>(s_win + s * Cfg::ROW);
+    const f2x2* trow = reinterpret_cast<const f2x2*>(s_tw2 + s * Cfg::TROW);
+    const f2x2* prow = reinterpret_cast<const f2x2*>(s_twP + s * Cfg::PROW);
+    const int partner = (32 - s) & 31;
+
+    const unsigned total = (unsigned)P.ncols * (unsigned)P.nstreams;
+    const unsigned gstep = gridDim.x * WARPS;
+    constexpr float scale = 0.5f;
+    auto stage = [&](unsigned g) { // both channels of frame g -> the two buffers (lane 0, after a __syncwarp())
+        const PkUnit un = pk_unit(P, g);
+        const float* a = P.samples + un.stream * P.stream_stride + un.st;
+        if (s == 0) bulk_copy2_g2s(xa, a, xb, a + P.channel_stride, M * 8, bar);
+#if defined(JADE_EMU)
+        __syncwarp();
+#endif
+    };
+    auto emit = [&](float p, uint32_t* pix, float* db) { emit_bin<MIX_SUM, WANT_DB>(p, scale, pix, db, P, s_pal); };
+
+    unsigned g = blockIdx.x * WARPS + warp;
+    if (g < total) stage(g);
+    for (; g < total; g += gstep) {
+        const PkUnit un = pk_unit(P, g);
+        const ColOut o = col_out(P, un.stream, un.j);
+
+        f2 va[32], vb[32];
+        mbar_wait(bar, copies & 1u);
+        ++copies;
+#pragma unroll
+        for (int jj = 0; jj < 16; jj += 2) {
+            const f2x2 wa = wrow[jj / 2], wb = wrow[(jj + 16) / 2];
+            const f2* za = xa + s;
+            const f2* zb = xb + s;
+            win_stage1(va, jj, za[32 * jj], wa.a, za[32 * (jj + 16)], wb.a);
+            win_stage1(va, jj + 1, za[32 * (jj + 1)], wa.b, za[32 * (jj + 17)], wb.b);
+            win_stage1(vb, jj, zb[32 * jj], wa.a, zb[32 * (jj + 16)], wb.a);
+            win_stage1(vb, jj + 1, zb[32 * (jj + 1)], wa.b, zb[32 * (jj + 17)], wb.b);
+        }
+        __syncwarp(); // every lane has read its samples before the transposes overwrite them
+        fft32_pk_after_stage1(va);
+        fft32_pk_after_stage1(vb);
+#pragma unroll
+        for (int k1 = 0; k1 < 32; ++k1) {
+            xa[k1 * Cfg::XROW + s] = va[k1];
+            xb[k1 * Cfg::XROW + s] = vb[k1];
+        }
+        __syncwarp();
+        f2 ua[32], ub[32];
+        {
+            const f2x2* ra = reinterpret_cast<const f2x2*>(xa + s * Cfg::XROW);
+            const f2x2* rb = reinterpret_cast<const f2x2*>(xb + s * Cfg::XROW);
+#pragma unroll
+            for (int jx = 0; jx < 32; jx += 2) {
+                const f2x2 ta = ra[jx / 2], tb = rb[jx / 2];
+                ua[brev(jx, 5)] = ta.a;
+                ua[brev(jx + 1, 5)] = ta.b;
+                ub[brev(jx, 5)] = tb.a;
+                ub[brev(jx + 1, 5)] = tb.b;
+            }
+        }
+        __syncwarp(); // the buffers are free again: stage the next frame of this warp
+        if (g + gstep < total) stage(g + gstep);
+        fft32_twisted2(ua, ub, trow);
+
+        uint32_t* p_lo = o.pix ? o.pix + (M - s) : nullptr; // bin k -> row M - k
+        uint32_t* p_hi = o.pix ? o.pix + s : nullptr;
+        float* d_lo = (WANT_DB && o.db) ? o.db + s : nullptr;
+        float* d_hi = (WANT_DB && o.db) ? o.db + (M - s) : nullptr;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const f2 zpa = sel2(s == 0, ua[(32 - q) & 31], shfl2(ua[31 - q], partner));
+            const f2 zpb = sel2(s == 0, ub[(32 - q) & 31], shfl2(ub[31 - q], partner));
+            const f2x2 wq2 = prow[q / 2];
+            const f2 wq = (q & 1) ? wq2.b : wq2.a;
+            const f2 Aa = add2(ua[q], conj2(zpa)), Ba = sub2(ua[q], conj2(zpa));
+            const f2 Ab = add2(ub[q], conj2(zpb)), Bb = sub2(ub[q], conj2(zpb));
+            const f2 Ta = cmul2(Ba, wq), Tb = cmul2(Bb, wq);
+            const f2 xpa = add2(Aa, Ta), xma = sub2(Aa, Ta);
+            const f2 xpb = add2(Ab, Tb), xmb = sub2(Ab, Tb);
+            // channel 0 first, channel 1 on top: the accumulation order of stft_pk2048_kernel
+            const float pl = fm(lo(xpb), lo(xpb), fm(hi(xpb), hi(xpb), fm(lo(xpa), lo(xpa), fm(hi(xpa), hi(xpa), 0.f))));
+            const float ph = fm(lo(xmb), lo(xmb), fm(hi(xmb), hi(xmb), fm(lo(xma), lo(xma), fm(hi(xma), hi(xma), 0.f))));
+            emit(pl, (!WANT_DB || p_lo) ? p_lo - 32 * q : nullptr, d_lo ? d_lo + 32 * q : nullptr);
+            emit(ph, (!WANT_DB || p_hi) ? p_hi + 32 * q : nullptr, d_hi ? d_hi - 32 * q : nullptr);
+        }
+        if (s == 0) { // bin 512 (lane 0, self-paired): X = 2 conj Z
+            const float a0 = lo(ua[16]), a1 = hi(ua[16]), b0 = lo(ub[16]), b1 = hi(ub[16]);
+            const float pm = fm(JADE_FMUL(4.0f, b0), b0, fm(JADE_FMUL(4.0f, b1), b1, fm(JADE_FMUL(4.0f, a0), a0, fm(JADE_FMUL(4.0f, a1), a1, 0.f))));
+            emit(pm, (!WANT_DB || o.pix) ? o.pix + 512 : nullptr, (WANT_DB && o.db) ? o.db + 512 : nullptr);
         }
     }
 }

@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -47,7 +48,11 @@ void run_pk_one(const KParams& P, int npal, int grid)
     const int block = (T == 32 ? jade::PkCfg::WARPS : jade::PkSmallCfg<2>::WARPS) * 32;
     if constexpr (T == 32) {
         // same routing as launch_stft: guard / cp.async staging (16-byte aligned) / LDG to registers (8-byte aligned)
+        // stereo kernel for AbsMean over two channels unless JADE_EMU_NOPAIR is set (tests cover both)
+        const bool pair_ok = MIXK == jade::MIX_SUM && P.channels == 2 && !getenv("JADE_EMU_NOPAIR");
         if (GUARD) jade_emu::launch(jade::stft_pk2048_kernel<MIXK, WDB, jade::PK_LD_GUARD>, grid, block, jade::PkCfg::smem_bytes(npal), P);
+        else if (P.aligned4 && pair_ok)
+            jade_emu::launch(jade::stft_pk2048x2_kernel<WDB>, grid, jade::PkPairCfg::WARPS * 32, jade::PkPairCfg::smem_bytes(npal), P);
         else if (P.aligned4) jade_emu::launch(jade::stft_pk2048_kernel<MIXK, WDB, jade::PK_LD_ASYNC>, grid, block, jade::PkCfg::smem_bytes(npal), P);
         else jade_emu::launch(jade::stft_pk2048_kernel<MIXK, WDB, jade::PK_LD_DIRECT>, grid, block, jade::PkCfg::smem_bytes(npal), P);
     }
