@@ -191,6 +191,7 @@ int upload(jade_engine* e, DevBuf& b, const void* src, size_t bytes)
 int choose_kernel(jade_engine* e)
 {
     KernelChoice kc;
+    e->has_mid = e->has_pair = false;
     const int N = e->N;
     const int mu = e->mixk;
     const bool po = e->general;
@@ -216,7 +217,6 @@ int choose_kernel(jade_engine* e)
         kc.fn_db = T == 32 ? jade_k::pk2048_kernel(mu, true, jade::PK_LD_ASYNC) : jade_k::pksmall_kernel(T, mu, true, false);
         ke.fn = T == 32 ? jade_k::pk2048_kernel(mu, true, jade::PK_LD_GUARD) : jade_k::pksmall_kernel(T, mu, true, true);
         if (!kc.fn || !kc.fn_db || !ke.fn) return fail(e, JADE_ERR_ARG, "unsupported fft_size %d", N);
-        e->has_mid = false;
         if (T == 32) {
             KernelChoice km = kc;
             snprintf(km.name, sizeof km.name, "pk2048-ldg");
@@ -231,7 +231,6 @@ int choose_kernel(jade_engine* e)
             e->kc_mid = km;
             e->has_mid = true;
             // stereo kernel: the two channels of a frame share every table read
-            e->has_pair = false;
             const int contributing = (e->cfg.mix_mode == JADE_MIX_LEFT || e->cfg.mix_mode == JADE_MIX_RIGHT) ? 1 : e->cfg.channels;
             if (mu == jade::MIX_SUM && contributing == 2) {
                 KernelChoice kp = kc;
@@ -1308,6 +1307,10 @@ int jade_host_free(void* p)
 }
 
 int64_t jade_kernel_launches(jade_engine* e) { return e ? (int64_t)e->launches.load() : 0; }
-const char* jade_kernel_name(jade_engine* e) { return (e && e->configured) ? e->kc.name : ""; }
+const char* jade_kernel_name(jade_engine* e)
+{
+    if (!e || !e->configured) return "";
+    return e->has_pair ? e->kc_pair.name : e->kc.name; // the kernel interior, aligned frames go to
+}
 
 } // extern "C"
