@@ -661,7 +661,9 @@ JADE_KERNEL(PkCfg::WARPS * 32, JADE_PK_CTAS) stft_pk2048_kernel(const KParams P)
 // (TMA staging as in PK_LD_ASYNC, one mbarrier completion for the two 8 KB copies); everything else goes to
 // stft_pk2048_kernel, whose per-channel arithmetic is the same code in the same order, so the results are bit-identical.
 // (The same pairing applied to two consecutive mono columns is slower than one transform per warp: 433 M vs 485 M
-// frames/s, gpurun_out/variants10.txt -- mono keeps stft_pk2048_kernel.)
+// frames/s, gpurun_out/variants10.txt -- mono keeps stft_pk2048_kernel.  Replacing the TMA staging by LDG.64 of the next
+// frame into the registers the split loop frees, which would save the 256 staging wavefronts, fits in 168 registers
+// but runs at 245 M instead of 291 M frames/s.)
 // ---------------------------------------------------------------------------------------------------------
 struct PkPairCfg {
     static constexpr int WARPS = 12;
@@ -763,8 +765,8 @@ JADE_KERNEL(PkPairCfg::WARPS * 32, 1) stft_pk2048x2_kernel(const KParams P)
                 ub[brev(jx + 1, 5)] = tb.b;
             }
         }
-        __syncwarp(); // the buffers are free again: stage the next frame of this warp
-        if (g + gstep < total) stage(g + gstep);
+        __syncwarp(); // the buffers are free again
+        if (g + gstep < total) stage(g + gstep); // stage the next frame of this warp
         fft32_twisted2(ua, ub, trow);
 
         uint32_t* p_lo = o.pix ? o.pix + (M - s) : nullptr; // bin k -> row M - k
