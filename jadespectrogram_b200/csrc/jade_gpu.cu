@@ -428,6 +428,7 @@ int launch_stft(jade_engine* e, KParams& P, cudaStream_t st)
     // packed kernels: interior, aligned frames (16 bytes: cp.async staging for N = 2048; 8 bytes: LDG.64); the rest goes
     // to the guarded-load instantiation
     if (!P.aligned2) return launch_one(e, e->kc_edge, P, st);
+    if (!e->has_mid && !P.aligned4) return launch_one(e, e->kc_edge, P, st); // N < 2048: the staged kernel or the guarded one
     static const bool force_ldg = [] { const char* v = getenv("JADE_PK_LOAD"); return v && !strcmp(v, "ldg"); }(); // experiments
     static const bool no_pair = [] { const char* v = getenv("JADE_PK_LOAD"); return v && !strcmp(v, "single"); }();
     const KernelChoice& main_kc = (e->has_mid && (!P.aligned4 || force_ldg)) ? e->kc_mid : ((e->has_pair && !no_pair) ? e->kc_pair : e->kc);

@@ -224,6 +224,8 @@ inline void bulk_copy2_g2s(void* dst0, const void* src0, void* dst1, const void*
     std::memcpy(dst0, src0, (size_t)bytes);
     std::memcpy(dst1, src1, (size_t)bytes);
 }
+inline void mbar_expect_tx(unsigned long long*, int) {}
+inline void bulk_copy_issue(void* dst, const void* src, int bytes, unsigned long long*) { std::memcpy(dst, src, (size_t)bytes); }
 inline void mbar_wait(unsigned long long*, unsigned) {}
 #else
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, int count)
@@ -238,6 +240,21 @@ __device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, int by
     const unsigned d = (unsigned)__cvta_generic_to_shared(dst), b = (unsigned)__cvta_generic_to_shared(bar);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d), "l"(src),
+                 "r"(bytes), "r"(b)
+                 : "memory");
+}
+// the same in two steps, for several copies issued by different lanes on one barrier: ONE lane announces the total
+// (mbar_expect_tx, after a __syncwarp()), then -- after another __syncwarp() -- any lane issues its copy
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, int bytes)
+{
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_issue(void* dst, const void* src, int bytes, unsigned long long* bar)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst), b = (unsigned)__cvta_generic_to_shared(bar);
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d), "l"(src),
                  "r"(bytes), "r"(b)
                  : "memory");

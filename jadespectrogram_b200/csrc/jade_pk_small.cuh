@@ -15,6 +15,14 @@
 #pragma once
 #include "jade_pk.cuh"
 
+// occupancy: JADE_PKS_WARPS warps per CTA, JADE_PKS_CTAS CTAs per SM
+#ifndef JADE_PKS_WARPS
+#define JADE_PKS_WARPS 8
+#endif
+#ifndef JADE_PKS_CTAS
+#define JADE_PKS_CTAS 2
+#endif
+
 namespace jade {
 
 template <int T>
@@ -22,7 +30,7 @@ struct PkSmallCfg {
     static constexpr int M = 32 * T, N = 2 * M, B = M + 1;
     static constexpr int F = 32 / T;
     static constexpr int H = T / 2;   // k2 values per pair half
-    static constexpr int WARPS = 8;
+    static constexpr int WARPS = JADE_PKS_WARPS;
     static constexpr int ROW = 34;    // f2 words per s-row of the window / inter-pass twiddle tables (32 + 16 B pad)
     static constexpr int PROW = 18;   // f2 words per s-row of the split-twiddle table (16 + 16 B pad)
     // per-frame tile (f2 words): 32 rows of T+1 for the transpose, reused as 16 rows of T+1 for the exchange; the stride
@@ -32,7 +40,8 @@ struct PkSmallCfg {
     static constexpr int off_twI = off_win + T * ROW * 8;
     static constexpr int off_twP = off_twI + T * ROW * 8;
     static constexpr int off_pal = off_twP + T * PROW * 8;
-    static JADE_HD int off_xch(int npal) { return off_pal + (npal * 4 + 15) / 16 * 16; }
+    static JADE_HD int off_bar(int npal) { return off_pal + (npal * 4 + 15) / 16 * 16; } // one mbarrier per warp
+    static JADE_HD int off_xch(int npal) { return off_bar(npal) + (WARPS * 8 + 15) / 16 * 16; }
     static JADE_HD int smem_bytes(int npal) { return off_xch(npal) + WARPS * F * FS * 8; }
 };
 
@@ -46,7 +55,7 @@ JADE_HD constexpr int lane0_partner(int q)
 }
 
 template <int T, int MIXK, bool WANT_DB, bool GUARD>
-JADE_KERNEL(PkSmallCfg<T>::WARPS * 32, 2) stft_pksmall_kernel(const KParams P)
+JADE_KERNEL(PkSmallCfg<T>::WARPS * 32, JADE_PKS_CTAS) stft_pksmall_kernel(const KParams P)
 {
     using Cfg = PkSmallCfg<T>;
     constexpr int M = Cfg::M, F = Cfg::F, H = Cfg::H, FS = Cfg::FS, TS = T + 1;
@@ -57,8 +66,10 @@ JADE_KERNEL(PkSmallCfg<T>::WARPS * 32, 2) stft_pksmall_kernel(const KParams P)
     f2* s_twI = reinterpret_cast<f2*>(sm + Cfg::off_twI);
     f2* s_twP = reinterpret_cast<f2*>(sm + Cfg::off_twP);
     uint32_t* s_pal = reinterpret_cast<uint32_t*>(sm + Cfg::off_pal);
+    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(sm + Cfg::off_bar(P.npal));
     f2* s_xch = reinterpret_cast<f2*>(sm + Cfg::off_xch(P.npal));
 
+    if (!GUARD && threadIdx.x < Cfg::WARPS) mbar_init(s_bar + threadIdx.x, 1);
     // ---- per-s tables: entry (s, index) at [s*ROW + index]
     for (int i = threadIdx.x; i < M; i += blockDim.x) {
         const int s = i % T, n1 = i / T;                         // m = s + T n1
@@ -87,31 +98,65 @@ JADE_KERNEL(PkSmallCfg<T>::WARPS * 32, 2) stft_pksmall_kernel(const KParams P)
 
     const unsigned groups = (unsigned)((P.ncols + F - 1) / F);
     const unsigned total = groups * (unsigned)P.nstreams;
+    const unsigned gstep = gridDim.x * Cfg::WARPS;
     int ch0, ch1;
     channel_range(P, ch0, ch1);
+    if (MIXK == MIX_NONE) ch1 = ch0 + 1;
     const float scale = (MIXK == MIX_SUM) ? (1.0f / (float)P.channels) : 1.0f;
+    unsigned long long* bar = s_bar + warp;
+    unsigned copies = 0; // staged groups of this warp waited for so far (mbarrier phase parity)
 
-    for (unsigned g = blockIdx.x * Cfg::WARPS + warp; g < total; g += gridDim.x * Cfg::WARPS) {
-        const int stream = (int)(g / groups);
-        int jrel = (int)(g - (unsigned)stream * groups) * F + f;
-        const bool active = jrel < P.ncols;
-        if (!active) jrel = P.ncols - 1; // transform the last column again, store nothing
-        const long long j = P.first_col + jrel;
-        const long long st = frame_start(P, j);
+    // frame of this lane in group gg: stream, column (clamped to the last one), first sample
+    auto frame_of = [&](unsigned gg, int& stream_, long long& j_, long long& st_, bool& active_) {
+        stream_ = (int)(gg / groups);
+        int jrel = (int)(gg - (unsigned)stream_ * groups) * F + f;
+        active_ = jrel < P.ncols;
+        if (!active_) jrel = P.ncols - 1; // transform the last column again, store nothing
+        j_ = P.first_col + jrel;
+        st_ = frame_start(P, j_);
+    };
+    // GUARD = false: interior frames starting on a multiple of 4 samples with 16-byte aligned channel bases
+    // (P.aligned4).  The TMA engine copies the F frames (8 KB together) a warp transforms next -- channel ch of group gg --
+    // into the warp's F tiles while the warp is still busy with the split and the epilogue of the previous ones: lane 0
+    // announces the bytes on the warp's mbarrier, then the first lane of every frame issues its cp.async.bulk.
+    auto stage = [&](unsigned gg, int ch) {
+        int stream_;
+        long long j_, st_;
+        bool act_;
+        frame_of(gg, stream_, j_, st_, act_);
+        if (lane == 0) mbar_expect_tx(bar, F * M * 8);
+        __syncwarp();
+        if (s == 0) bulk_copy_issue(xw, P.samples + stream_ * P.stream_stride + ch * P.channel_stride + st_, M * 8, bar);
+#if defined(JADE_EMU)
+        __syncwarp();
+#endif
+    };
+
+    unsigned g = blockIdx.x * Cfg::WARPS + warp;
+    if (!GUARD && g < total) stage(g, ch0);
+    for (; g < total; g += gstep) {
+        int stream;
+        long long j, st;
+        bool active;
+        frame_of(g, stream, j, st, active);
 
         float alo[16], ahi[16], amid = 0.f; // bins k(q) = s + T i + 32 k2 / M - k(q) / M/2 (lane s = 0)
 #pragma unroll
         for (int q = 0; q < 16; ++q) alo[q] = ahi[q] = 0.f;
 
-        for (int ch = ch0; ch < (MIXK == MIX_NONE ? ch0 + 1 : ch1); ++ch) {
+        for (int ch = ch0; ch < ch1; ++ch) {
             const float* x = P.samples + stream * P.stream_stride + ch * P.channel_stride;
             f2 v[32];
+            if (!GUARD) {
+                mbar_wait(bar, copies & 1u);
+                ++copies;
+            }
 #pragma unroll
             for (int jj = 0; jj < 16; jj += 2) { // n1 = jj, jj+1 paired with n1 + 16
                 const f2x2 wa = wrow[jj / 2], wb = wrow[(jj + 16) / 2];
                 f2 xa0, xa1, xb0, xb1;
                 if (!GUARD) {
-                    const f2* xz = reinterpret_cast<const f2*>(x + st) + s;
+                    const f2* xz = xw + s; // staged frame: z[m] at word m of the lane's tile
                     xa0 = xz[T * jj];
                     xa1 = xz[T * (jj + 1)];
                     xb0 = xz[T * (jj + 16)];
@@ -129,6 +174,7 @@ JADE_KERNEL(PkSmallCfg<T>::WARPS * 32, 2) stft_pksmall_kernel(const KParams P)
                 win_stage1(v, jj, xa0, wa.a, xb0, wb.a);
                 win_stage1(v, jj + 1, xa1, wa.b, xb1, wb.b);
             }
+            if (!GUARD) __syncwarp(); // every lane has read its samples before the transpose overwrites them
             fft32_pk_after_stage1(v);
 #pragma unroll
             for (int k1 = 0; k1 < 32; k1 += 2) {
@@ -154,10 +200,18 @@ JADE_KERNEL(PkSmallCfg<T>::WARPS * 32, 2) stft_pksmall_kernel(const KParams P)
                 for (int q = 0; q < 16; ++q) xw[(15 - q) * TS + T] = u[lane0_partner<T>(q)];
             }
             __syncwarp();
+            f2 zpv[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) zpv[q] = ex_rd[(15 - q) * TS];
+            __syncwarp(); // the tiles are free again
+            if (!GUARD) { // stage what this warp transforms next: the next channel of this group, or its next group
+                if (ch + 1 < ch1) stage(g, ch + 1);
+                else if (g + gstep < total) stage(g + gstep, ch0);
+            }
 #pragma unroll
             for (int q = 0; q < 16; ++q) {
                 const int uq = (q / H) * T + (q % H);
-                const f2 zp = ex_rd[(15 - q) * TS];
+                const f2 zp = zpv[q];
                 const f2x2 wq = prow[q / 2];
                 const f2 A = add2(u[uq], conj2(zp));  // Z[k] + conj Z[M-k]
                 const f2 Bv = sub2(u[uq], conj2(zp)); // Z[k] - conj Z[M-k]
@@ -170,7 +224,6 @@ JADE_KERNEL(PkSmallCfg<T>::WARPS * 32, 2) stft_pksmall_kernel(const KParams P)
                 const float a = lo(u[H]), b = hi(u[H]);
                 amid = fm(JADE_FMUL(4.0f, a), a, fm(JADE_FMUL(4.0f, b), b, amid));
             }
-            __syncwarp();
         }
 
         const ColOut o = active ? col_out(P, stream, j) : ColOut{nullptr, nullptr};

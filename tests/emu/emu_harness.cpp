@@ -166,7 +166,7 @@ extern "C" int emu_render(const jade_config* cin, const int32_t* palette, int np
         long long lo = j0, hi = j1;
         while (lo < j1 && start(lo) < 0) ++lo;
         while (hi > lo && start(hi - 1) + N > nsamples) --hi;
-        if (!P.aligned2) lo = hi = j0; // everything through the guarded instantiation
+        if (!P.aligned2 || (T < 32 && !P.aligned4)) lo = hi = j0; // everything through the guarded instantiation
         auto sub = [&](long long a, long long b) {
             KParams Q = P;
             Q.first_col = a;

@@ -70,6 +70,19 @@ def test_emulated_pk2048_pair_and_single(monkeypatch, ch, mix, nopair):
 _PAIR_RESULTS = {}
 
 
+@pytest.mark.parametrize("N,hop,ch,ncols", [(1024, 512, 1, 70), (1024, 256, 2, 45), (256, 64, 2, 150), (128, 32, 1, 301)])
+def test_emulated_pksmall_staging_chain(N, hop, ch, ncols):
+    """N <= 1024 packed kernels with several column groups per warp: the TMA staging of the next channel / next group
+    (F frames per warp on one mbarrier), including a padded last group (odd column counts)."""
+    x = signals.streams(2, ch, hop * (ncols - 1) + 64, 48000.0)
+    pal = O.Palette(256, O.PAL["jade"]).table()
+    db, pix = E.render(_cfg(N, hop, ch, "hann", "absmean"), pal, -50.0, 50.0, x, 0, ncols, N // 2 + 1, grid=1)
+    for s in range(x.shape[0]):
+        odb, opix = O.render_batch(x[s], fft_size=N, hop=hop, window="hann", mix="absmean", ncols=ncols)
+        parity.check_db(db[s], odb, N, f"stream {s}")
+        parity.check_pixels(pix[s], opix, odb[:, ::-1], -50.0, 50.0, 256, f"stream {s}")
+
+
 @pytest.mark.parametrize("extra,want_db", [(0, True), (0, False), (2, True), (1, True)])
 def test_emulated_pk2048_prefetch_chain(extra, want_db):
     """N = 2048 with several frames per warp: the cp.async staging of the next channel / next frame (16-byte aligned
