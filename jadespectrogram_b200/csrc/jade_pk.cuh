@@ -680,7 +680,9 @@ JADE_KERNEL(PkCfg::WARPS * 32, JADE_PK_CTAS) stft_pk2048_kernel(const KParams P)
 // (The same pairing applied to two consecutive mono columns is slower than one transform per warp: 433 M vs 485 M
 // frames/s, gpurun_out/variants10.txt -- mono keeps stft_pk2048_kernel.  Replacing the TMA staging by LDG.64 of the next
 // frame into the registers the split loop frees, which would save the 256 staging wavefronts, fits in 168 registers
-// but runs at 245 M instead of 291 M frames/s.)
+// but runs at 245 M instead of 291 M frames/s.  A per-warp sample ring for mono renderings -- a warp walks consecutive
+// columns and copies only the hop new samples of each, 1 KB instead of 8 KB at hop 256 -- changes nothing: 484 M vs
+// 486 M frames/s, gpurun_out/variants13.txt; the staging writes are not on the critical path.)
 // ---------------------------------------------------------------------------------------------------------
 struct PkPairCfg {
     static constexpr int WARPS = 12;
