@@ -200,6 +200,11 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # pinned host buffers of the e2e leg on the GPU's own NUMA node (no-op on single-node boxes)
+    orig_affinity = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
+    props = torch.cuda.get_device_properties(local)
+    numa_node = sharding.bind_host_to_gpu_node(getattr(props, "pci_domain_id", 0), getattr(props, "pci_bus_id", 0),
+                                               getattr(props, "pci_device_id", 0))
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -279,9 +284,11 @@ def run_ours(args):
         eng.render_batch(h_in, out_pix=h_pix)
     e2e_s = time.perf_counter() - t0
     e2e_value = Se * ncols * e2e_steps * world / sharding.reduce_max(e2e_s, dev)
+    if numa_node is not None and orig_affinity is not None:
+        os.sched_setaffinity(0, orig_affinity)  # the CPU baseline leg below uses every host core
     check = int(h_pix[0, ncols // 2].astype(np.uint64).sum())  # the step's result is read on the host
     e2e = dict(value=e2e_value, unit="frames/s", h2d_bytes_per_step=int(h_in.nbytes), d2h_bytes_per_step=int(h_pix.nbytes),
-               steps=e2e_steps, streams_per_step=Se, api="jade_render_batch (pinned host buffers)", checksum=check)
+               steps=e2e_steps, streams_per_step=Se, api="jade_render_batch (pinned host buffers)", host_numa_node=numa_node, checksum=check)
     host_free(h_in)
     host_free(h_pix)
 

@@ -55,6 +55,40 @@ def input_range(col_lo, col_hi, nsamples, fft_size, hop, frames_per_block=1, blo
     return a, max(a, b)
 
 
+def parse_cpulist(text):
+    """'0-3,8,10-11' -> {0,1,2,3,8,10,11} (sysfs cpulist format)."""
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_host_to_gpu_node(pci_domain, pci_bus, pci_device, sysfs="/sys/bus/pci/devices"):
+    """One process per GPU: run this process (and so first-touch its pinned host buffers, the H2D source and D2H
+    destination of `jade_render_batch`) on the CPUs of the NUMA node the GPU's PCIe root hangs off, so that DMA does not
+    cross the socket interconnect.  Does nothing when the machine reports no NUMA node for the device (single-socket
+    boxes, VMs without a virtual topology) or when the node's CPUs are not in the current affinity mask.
+    Returns the NUMA node bound to, or None."""
+    import os
+    base = f"{sysfs}/{pci_domain:04x}:{pci_bus:02x}:{pci_device:02x}.0"
+    try:
+        node = int(open(f"{base}/numa_node").read())
+        local = parse_cpulist(open(f"{base}/local_cpulist").read())
+    except (OSError, ValueError):
+        return None
+    if node < 0 or not hasattr(os, "sched_getaffinity"):
+        return None
+    allowed = os.sched_getaffinity(0)
+    target = local & allowed
+    if not target or target == allowed:
+        return None
+    os.sched_setaffinity(0, target)
+    return node
+
+
 def reduce_max(value, device=None):
     """MAX over ranks of a python float (device time of the slowest rank); identity when not distributed."""
     import torch

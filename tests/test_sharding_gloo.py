@@ -93,3 +93,29 @@ def test_partition_rules():
     assert (a0, b0) == (0, 99 * 512) and a1 == 100 * 512 - 2048 and b0 - a1 == 2048 - 512
     # three streams on eight ranks: one stream each, the rest idle
     assert [sharding.plan(3, 50, 8, r).empty for r in range(8)] == [False] * 3 + [True] * 5
+
+
+def test_bind_host_to_gpu_node_reads_sysfs(tmp_path):
+    """NUMA binding helper: parses the sysfs cpulist, ignores devices without a node, never widens the affinity mask."""
+    import os
+    from jadespectrogram_b200 import sharding
+    assert sharding.parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    dev = tmp_path / "0000:d1:00.0"
+    dev.mkdir()
+    (dev / "numa_node").write_text("-1\n")
+    (dev / "local_cpulist").write_text("0-1\n")
+    before = os.sched_getaffinity(0)
+    assert sharding.bind_host_to_gpu_node(0, 0xD1, 0, sysfs=str(tmp_path)) is None      # no NUMA node reported
+    assert sharding.bind_host_to_gpu_node(0, 0x17, 0, sysfs=str(tmp_path)) is None      # no such device
+    assert os.sched_getaffinity(0) == before
+    (dev / "numa_node").write_text("1\n")
+    (dev / "local_cpulist").write_text(",".join(str(c) for c in sorted(before)) + "\n")
+    assert sharding.bind_host_to_gpu_node(0, 0xD1, 0, sysfs=str(tmp_path)) is None      # node covers every allowed CPU
+    if len(before) > 1:
+        one = min(before)
+        (dev / "local_cpulist").write_text(f"{one},100000\n")
+        try:
+            assert sharding.bind_host_to_gpu_node(0, 0xD1, 0, sysfs=str(tmp_path)) == 1
+            assert os.sched_getaffinity(0) == {one}
+        finally:
+            os.sched_setaffinity(0, before)
