@@ -2,8 +2,10 @@
 //
 // One CTA of R1 warps transforms one frame of M = 1024 R1 complex points z[m] = x[2m] + i x[2m+1] that live in shared
 // memory (BASELINE configs[2]: N = 16384 -> 64 KB; "large-FFT smem staging"):
-//   column pass : thread owns columns n2 (32/R1 of them), loads z[n2 + 1024 n1] straight from global memory with the
-//                 window multiply fused into the first radix-2 stage, radix-R1 DFT in registers, twiddle W_M^(n2 k1),
+//   staging     : interior, 16-byte aligned frames are copied into the row matrix by the TMA engine (cp.async.bulk, R1 rows
+//                 of 8 KB, one mbarrier) while the CTA is still in the epilogue of the previous frame;
+//   column pass : thread owns columns n2 (32/R1 of them), reads z[n2 + 1024 n1] from the staged rows (or straight from
+//                 global memory for boundary / unaligned frames) with the window multiply fused into the first radix-2 stage, radix-R1 DFT in registers, twiddle W_M^(n2 k1),
 //                 row k1 of the shared-memory matrix;
 //   row pass    : warp k1 transforms its 1024-point row with the register code of the N = 2048 kernel (radix-32,
 //                 twiddle, in-place XOR-swizzled transpose, radix-32) and leaves it in natural order;
@@ -33,7 +35,9 @@ struct PkCtaCfg {
     static constexpr int off_twI = off_row + R1 * RS * 8;
     static constexpr int off_pal = off_twI + 32 * TROW * 8;
     static JADE_HD int off_spec(int npal) { return off_pal + (npal * 4 + 15) / 16 * 16; }
-    static JADE_HD int smem_bytes(int npal, bool general) { return off_spec(npal) + (general ? ((B + 3) / 4) * 16 : 0); }
+    // stft_pkcta_kernel (general == false): one mbarrier (frame staging) where the general kernels keep their spectrum
+    static JADE_HD int off_bar(int npal) { return off_spec(npal); }
+    static JADE_HD int smem_bytes(int npal, bool general) { return off_spec(npal) + (general ? ((B + 3) / 4) * 16 : 16); }
     // two-half kernel (N = 4096 R1): + the pooled-row table
     static JADE_HD int smem_bytes2(int npal, int pooled_rows) { return off_spec(npal) + (pooled_rows * 8 + 15) / 16 * 16; }
 };
@@ -124,31 +128,72 @@ JADE_KERNEL(32 * R1, PkCtaCfg<R1>::MINB) stft_pkcta_kernel(const KParams P)
     f2* s_twI = reinterpret_cast<f2*>(sm + Cfg::off_twI);
     uint32_t* s_pal = reinterpret_cast<uint32_t*>(sm + Cfg::off_pal);
 
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(sm + Cfg::off_bar(P.npal));
+
     const int t = threadIdx.x;
     stage_row_twiddles<R1>(s_twI, P.twI);
     for (int i = t; i < P.npal; i += THREADS) s_pal[i] = P.palette[i];
+    if (t == 0) mbar_init(bar, 1);
     __syncthreads();
 
     const unsigned total = (unsigned)P.ncols * (unsigned)P.nstreams;
     int ch0, ch1;
     channel_range(P, ch0, ch1);
+    if (MIXK == MIX_NONE) ch1 = ch0 + 1;
     const f2* JADE_RESTRICT winp = reinterpret_cast<const f2*>(P.window);
     const float scale = (MIXK == MIX_SUM) ? (1.0f / (float)P.channels) : 1.0f;
 
+    // Interior frames on a multiple of 4 samples (P.aligned4) are STAGED: the TMA engine copies the frame's R1 rows of
+    // 1024 complex samples into the row matrix (cp.async.bulk, one mbarrier completion) while the CTA is still in the
+    // epilogue of the previous frame, and the column pass then works in place on shared memory.
+    auto frame_of = [&](unsigned gg, int& stream_, long long& j_, long long& st_, bool& staged_) {
+        stream_ = (int)(gg / (unsigned)P.ncols);
+        j_ = P.first_col + (gg - (unsigned)stream_ * (unsigned)P.ncols);
+        st_ = frame_start(P, j_);
+        // (R1 = 16: rows of 1025 words are only 8-byte aligned, cp.async.bulk needs 16 -- N = 32768 keeps the global loads)
+        staged_ = (Cfg::RS % 2 == 0) && P.aligned4 && st_ >= 0 && st_ + N <= P.nsamples;
+    };
+    auto stage = [&](const float* src) { // thread 0, after a __syncthreads(): rows n1 = 0 .. R1-1 of the frame at src
+        if (t == 0) {
+            mbar_expect_tx(bar, M * 8);
+#pragma unroll
+            for (int n1 = 0; n1 < R1; ++n1) bulk_copy_issue(rowbuf + n1 * Cfg::RS, src + 2048 * n1, 8192, bar);
+        }
+#if defined(JADE_EMU)
+        __syncthreads();
+#endif
+    };
+    unsigned copies = 0;
+    {
+        int stream_;
+        long long j_, st_;
+        bool staged_ = false;
+        if (blockIdx.x < total) frame_of(blockIdx.x, stream_, j_, st_, staged_);
+        if (staged_) stage(P.samples + stream_ * P.stream_stride + ch0 * P.channel_stride + st_);
+    }
+
     for (unsigned g = blockIdx.x; g < total; g += gridDim.x) {
-        const int stream = (int)(g / (unsigned)P.ncols);
-        const long long j = P.first_col + (g - (unsigned)stream * (unsigned)P.ncols);
-        const long long st = frame_start(P, j);
+        int stream;
+        long long j, st;
+        bool staged;
+        frame_of(g, stream, j, st, staged);
         const bool fast = P.aligned2 && st >= 0 && st + N <= P.nsamples;
 
         float alo[16], ahi[16], amid = 0.f; // bins t + THREADS q / M - (t + THREADS q) / M/2 (thread 0)
 #pragma unroll
         for (int q = 0; q < 16; ++q) alo[q] = ahi[q] = 0.f;
 
-        for (int ch = ch0; ch < (MIXK == MIX_NONE ? ch0 + 1 : ch1); ++ch) {
+        for (int ch = ch0; ch < ch1; ++ch) {
             const float* x = P.samples + stream * P.stream_stride + ch * P.channel_stride;
             const long long ns = P.nsamples;
-            if (fast) {
+            if (staged) {
+                mbar_wait(bar, copies & 1u);
+                ++copies;
+                cta_fft_pk<R1>(rowbuf, s_twI, P.twA, [&](int m, f2& xv, f2& wv) {
+                    xv = rowbuf[(m >> 10) * Cfg::RS + (m & 1023)]; // the thread's own column: replaced in place below
+                    wv = winp[m];
+                });
+            } else if (fast) {
                 const f2* xz = reinterpret_cast<const f2*>(x + st);
                 cta_fft_pk<R1>(rowbuf, s_twI, P.twA, [&](int m, f2& xv, f2& wv) {
                     xv = xz[m];
@@ -180,6 +225,16 @@ JADE_KERNEL(32 * R1, PkCtaCfg<R1>::MINB) stft_pkcta_kernel(const KParams P)
                 amid = fm(JADE_FMUL(4.0f, a), a, fm(JADE_FMUL(4.0f, b), b, amid));
             }
             __syncthreads();
+            // the row matrix is free: stage what this CTA transforms next (covered by the epilogue below)
+            if (ch + 1 < ch1) {
+                if (staged) stage(x + P.channel_stride + st);
+            } else if (g + gridDim.x < total) {
+                int stream_;
+                long long j_, st_;
+                bool staged_;
+                frame_of(g + gridDim.x, stream_, j_, st_, staged_);
+                if (staged_) stage(P.samples + stream_ * P.stream_stride + ch0 * P.channel_stride + st_);
+            }
         }
 
         const ColOut o = col_out(P, stream, j);

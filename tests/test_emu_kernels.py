@@ -99,6 +99,20 @@ def test_emulated_pk2048_prefetch_chain(extra, want_db):
         parity.check_pixels(pix[s], opix, odb[:, ::-1], -50.0, 50.0, 256, f"stream {s}")
 
 
+@pytest.mark.parametrize("N,hop,ch,extra", [(4096, 1024, 2, 0), (8192, 2048, 1, 0), (4096, 1024, 1, 2)])
+def test_emulated_pkcta_frame_staging(N, hop, ch, extra):
+    """N >= 4096 packed kernels, several frames per CTA: interior frames are staged into the row matrix by the TMA engine
+    (next channel / next frame while the epilogue runs), boundary frames and 8-byte-aligned inputs (extra = 2) take the
+    global-load paths; the sequence mixes both."""
+    ncols = 11
+    x = signals.streams(1, ch, hop * (ncols - 1) + 64 + extra, 48000.0)
+    pal = O.Palette(256, O.PAL["jade"]).table()
+    db, pix = E.render(_cfg(N, hop, ch, "hann", "absmean"), pal, -50.0, 50.0, x, 0, ncols, N // 2 + 1, grid=1)
+    odb, opix = O.render_batch(x[0], fft_size=N, hop=hop, window="hann", mix="absmean", ncols=ncols)
+    parity.check_db(db[0], odb, N)
+    parity.check_pixels(pix[0], opix, odb[:, ::-1], -50.0, 50.0, 256)
+
+
 def test_emulated_general_epilogue_options():
     N, hop = 1024, 256
     x = signals.streams(1, 2, hop * 8, 48000.0)
