@@ -69,15 +69,18 @@ JADE_DEVICE void cta_fft_pk(f2* rowbuf, const f2* s_twI, const cpx* JADE_RESTRIC
             win_stage1<R1>(a, j, xa, wa, xb, wb);
         }
         fft_pk_after_stage1<R1>(a);
-#pragma unroll
-        for (int k1 = 0; k1 < R1; ++k1) {
-            if (k1 == 0) {
-                rowbuf[n2] = a[0];
-            } else {
-                const cpx w = twA[k1 * 1024 + n2];
-                rowbuf[k1 * RS + n2] = cmul2(a[k1], pk(w.x, w.y));
-            }
+        // twiddles W_M^(n2 k1), k1 = 1 .. R1-1: one table value (k1 = 1) per column, the others by squaring / one more
+        // product (depth <= log2 R1, a few ulp) -- R1 - 2 fewer L2 round trips per column in a latency-bound kernel
+        f2 wk[R1];
+        {
+            const cpx w = twA[1024 + n2];
+            wk[1] = pk(w.x, w.y);
         }
+#pragma unroll
+        for (int k1 = 2; k1 < R1; ++k1) wk[k1] = (k1 & 1) ? cmul2(wk[k1 - 1], wk[1]) : cmul2(wk[k1 / 2], wk[k1 / 2]);
+        rowbuf[n2] = a[0];
+#pragma unroll
+        for (int k1 = 1; k1 < R1; ++k1) rowbuf[k1 * RS + n2] = cmul2(a[k1], wk[k1]);
     }
     __syncthreads();
     // row pass: warp `warp` transforms row k1 = warp (1024 points) in place
