@@ -309,7 +309,21 @@ def run_ours(args):
                 ts.append((t1 - t0) * 1e6)
         ts.sort()
         lat = dict(p50_us=ts[len(ts) // 2], p99_us=ts[int(len(ts) * 0.99)], blocks=nblk, block_samples=512,
-                   path="jade_push_samples + jade_fetch_columns (1 column per block), host timer around both calls")
+                   path="jade_push_samples + jade_fetch_columns (1 column per block), host timer around both calls",
+                   caller="python (ctypes wrappers)")
+        # The plugin's host is C++: the same loop from a native caller of the C ABI (tools/native/latency_probe.cpp) is the
+        # headline; the Python numbers above stay as `python_*` (ctypes / numpy add a few microseconds per block).
+        probe = ROOT / "tools" / "native" / "latency_probe"
+        if probe.exists():
+            try:
+                out = subprocess.run([str(probe), str(nblk), str(local)], capture_output=True, text=True, timeout=120)
+                nat = json.loads(out.stdout.strip().splitlines()[-1])
+                lat = dict(p50_us=nat["p50_us"], p99_us=nat["p99_us"], push_p50_us=nat["push_p50_us"],
+                           fetch_p50_us=nat["fetch_p50_us"], blocks=nat["blocks"], block_samples=512, path=lat["path"],
+                           caller="native C++ (tools/native/latency_probe.cpp)", python_p50_us=lat["p50_us"],
+                           python_p99_us=lat["p99_us"])
+            except Exception as ex:  # keep the Python measurement
+                lat["native_probe_error"] = str(ex)[:200]
 
     if rank == 0:
         peak, peak_src = measured_peak()

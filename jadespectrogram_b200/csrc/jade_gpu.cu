@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -146,6 +147,7 @@ struct jade_engine {
     long long frames_done = 0;  // frames analysed (or skipped while paused): next frame index
     long long emitted = 0;      // columns published to the ring (the reference's running m_memCounter)
     long long fetched = 0;      // columns handed to fetch
+    long long poll_from = 0;    // ring columns >= poll_from were zeroed before their launch: fetch may poll them (see fetch)
     int stage_slot = 0;
     size_t stage_slot_bytes = 0;
     cudaEvent_t stage_ev[kStageSlots] = {};
@@ -400,7 +402,23 @@ int launch_one(jade_engine* e, const KernelChoice& kc, KParams& P, cudaStream_t 
     }
     void* args[] = {(void*)&P};
     const kernel_fn fn = (P.db && kc.fn_db) ? kc.fn_db : kc.fn;
-    CU(e, cudaLaunchKernel((const void*)fn, dim3(grid), dim3(kc.threads), args, kc.smem, st));
+    if (P.ring_w > 0) {
+        // streaming push: programmatic dependent launch behind ingest_kernel (every STFT kernel calls grid_dep_wait()
+        // after its table prologue, jade_kernels.cuh)
+        cudaLaunchConfig_t lc = {};
+        lc.gridDim = dim3(grid);
+        lc.blockDim = dim3(kc.threads);
+        lc.dynamicSmemBytes = (size_t)kc.smem;
+        lc.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        lc.attrs = at;
+        lc.numAttrs = 1;
+        CU(e, cudaLaunchKernelExC(&lc, (const void*)fn, args));
+    } else {
+        CU(e, cudaLaunchKernel((const void*)fn, dim3(grid), dim3(kc.threads), args, kc.smem, st));
+    }
     e->launches++;
     return 0;
 }
@@ -489,6 +507,7 @@ int reset_stream_state(jade_engine* e)
     e->emitted = 0;
     e->frames_done = 0;
     e->fetched = 0;
+    e->poll_from = 0;
     // ring filled with -120 dB (Spectrogram.cpp:223); pixel ring with the colour of -120 dB
     std::vector<float> init((size_t)e->W * e->B, -120.0f);
     CU(e, cudaMemcpyAsync(e->d_dbring.p, init.data(), init.size() * 4, cudaMemcpyHostToDevice, e->stream));
@@ -887,7 +906,7 @@ int jade_push_samples(jade_engine* e, const float* const* planar, int nch, int n
         const long long next_start = frame_start_abs(c, e->frames_done); // oldest sample still needed
         long long from = next_start - e->hist_base_abs;
         if (from < 0) from = 0;
-        from &= ~1LL; // keep frame starts even relative to the buffer
+        from &= ~3LL; // keep frame starts 16-byte aligned relative to the buffer (TMA-staged kernels)
         keep = (int)(e->hist_fill - from);
         slide_from = from;
         e->hist_base_abs += from;
@@ -937,6 +956,16 @@ int jade_push_samples(jade_engine* e, const float* const* planar, int nch, int n
             P.db = (float*)e->d_dbring.p;
             P.ring_w = e->W;
             P.ring_col0 = e->emitted + skip;
+            // Arm the columns for polling: every pixel carries alpha 0xFF (bake_pixel), so a zeroed slot that has become
+            // non-zero everywhere has been written completely -- jade_fetch_columns can hand it out without waiting for
+            // the kernel to retire and its event to signal.  Only for a handful of columns of a long ring (the slots
+            // cannot still be the target of an earlier launch); otherwise fetch falls back to the event.
+            if (n <= 8 && e->W >= 64) {
+                uint32_t* ring = (uint32_t*)e->h_pixring.p;
+                for (long long i = 0; i < n; ++i) memset(ring + (size_t)((P.ring_col0 + i) % e->W) * e->R, 0, (size_t)e->R * 4);
+            } else {
+                e->poll_from = e->emitted + skip + n;
+            }
             if (int r = launch_stft(e, P, e->stream)) return r;
             e->emitted += skip + n;
         }
@@ -951,7 +980,7 @@ int jade_fetch_columns(jade_engine* e, uint32_t* pixels, float* db, int max_cols
     if (!e || !ncols) return fail(e, JADE_ERR_ARG, "null argument");
     if (!e->configured) return fail(e, JADE_ERR_STATE, "engine not configured");
     *ncols = 0;
-    long long from, to;
+    long long from, to, poll_from;
     {
         std::lock_guard<std::mutex> lk(e->mu);
         from = e->fetched;
@@ -959,13 +988,33 @@ int jade_fetch_columns(jade_engine* e, uint32_t* pixels, float* db, int max_cols
         if (to - from > e->W) from = to - e->W;
         if (max_cols >= 0 && to - from > max_cols) from = to - max_cols;
         e->fetched = to;
+        poll_from = e->poll_from;
     }
     if (first_col) *first_col = from;
     if (to <= from) return JADE_OK;
     CU(e, cudaSetDevice(e->device));
-    CU(e, cudaEventSynchronize(e->last_push_ev));
     const int W = e->W, R = e->R, B = e->B;
     const uint32_t* ring = (const uint32_t*)e->h_pixring.p;
+    // Columns armed by jade_push_samples are complete once no pixel of their (pinned, device-mapped) slot is zero: poll
+    // instead of waiting for the stream event (saves the kernel-retire + event-signal latency of the real-time path).
+    bool landed = !db && from >= poll_from;
+    if (landed) {
+        const auto t_end = std::chrono::steady_clock::now() + std::chrono::milliseconds(20);
+        for (long long j = from; j < to && landed; ++j) {
+            const volatile uint32_t* slot = ring + (size_t)(j % W) * R;
+            for (;;) {
+                int r = R - 1;
+                while (r >= 0 && slot[r] != 0u) --r;
+                if (r < 0) break;
+                if (std::chrono::steady_clock::now() > t_end) { // not expected: let the event decide
+                    landed = false;
+                    break;
+                }
+            }
+        }
+        std::atomic_thread_fence(std::memory_order_acquire);
+    }
+    if (!landed) CU(e, cudaEventSynchronize(e->last_push_ev));
     for (long long j = from; j < to; ++j) {
         const long long slot = j % W;
         if (pixels) memcpy(pixels + (size_t)(j - from) * R, ring + (size_t)slot * R, (size_t)R * 4);

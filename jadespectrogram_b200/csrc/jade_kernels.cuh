@@ -110,6 +110,19 @@ struct KParams {
     const cpx* twH;         // [M/2+1]  W_{N/2}^k  (split of the half-size real FFTs)
 };
 
+// Programmatic dependent launch (streaming path): the engine launches the STFT kernel of a push with
+// cudaLaunchAttributeProgrammaticStreamSerialization right behind ingest_kernel, which releases its dependents at once, so
+// that the STFT kernel's table prologue overlaps the ingest; grid_dep_wait() -- after the prologue, before the first read
+// of the samples -- blocks until the ingest grid has completed and its writes are visible.  Both are no-ops for a
+// kernel launched the ordinary way.
+#if defined(JADE_EMU)
+inline void grid_dep_wait() {}
+inline void grid_dep_launch() {}
+#else
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+
 // 10*log10(p + 1e-11) (Spectrogram.cpp:36,107).  Fast: one MUFU.LG2 + one FMUL (|err| ~ 1e-5 dB).
 JADE_DEVICE float to_db_fast(float p) { return JADE_FMUL(3.01029995663981195f, JADE_LOG2F(JADE_FADD(p, 1e-11f))); }
 // Exactly the reference's arithmetic: float add, double log10, double multiply, float store.
@@ -364,6 +377,7 @@ JADE_KERNEL(WARP_KERNEL_WARPS * 32, (T >= 4 && !GENERAL) ? 2 : 1) stft_warp_kern
     for (int i = threadIdx.x; i <= M; i += blockDim.x) s_twP[i] = P.twP[i];
     for (int i = threadIdx.x; i < P.npal; i += blockDim.x) s_pal[i] = P.palette[i];
     __syncthreads();
+    grid_dep_wait();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int f = lane / T, s = lane % T;
@@ -537,6 +551,7 @@ JADE_KERNEL(32 * R1, 1) stft_cta_kernel(const KParams P)
     for (int i = t; i < 1024; i += THREADS) s_twI[i] = P.twI[i];
     for (int i = t; i < P.npal; i += THREADS) s_pal[i] = P.palette[i];
     __syncthreads();
+    grid_dep_wait();
 
     const unsigned total = (unsigned)P.ncols * (unsigned)P.nstreams;
     int ch0, ch1;
@@ -630,6 +645,7 @@ JADE_KERNEL(256) recolor_kernel(const KParams P, const float* dbcols, long long 
 JADE_KERNEL(256) ingest_kernel(float* hist, long long channel_stride, int channels, const float* stage, int n,
                                long long write_pos, long long slide_from, int keep)
 {
+    grid_dep_launch(); // the STFT kernel behind may start its prologue now; it waits for this grid before reading hist
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, step = gridDim.x * blockDim.x;
     for (int ch = 0; ch < channels; ++ch) {
         float* h = hist + ch * channel_stride;

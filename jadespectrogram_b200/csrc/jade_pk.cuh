@@ -527,6 +527,7 @@ JADE_KERNEL(PkCfg::WARPS * 32, JADE_PK_CTAS) stft_pk2048_kernel(const KParams P)
     }
     for (int i = threadIdx.x; i < P.npal; i += blockDim.x) s_pal[i] = P.palette[i];
     __syncthreads();
+    grid_dep_wait();
 
     const int s = threadIdx.x & 31, warp = threadIdx.x >> 5;
     f2* xw = s_xch + warp * Cfg::XCH;
@@ -719,6 +720,7 @@ JADE_KERNEL(PkPairCfg::WARPS * 32, 1) stft_pk2048x2_kernel(const KParams P)
     }
     for (int i = threadIdx.x; i < P.npal; i += blockDim.x) s_pal[i] = P.palette[i];
     __syncthreads();
+    grid_dep_wait();
 
     const int s = threadIdx.x & 31, warp = threadIdx.x >> 5;
     f2* xa = s_xch + warp * 2 * XCH; // buffer of channel 0

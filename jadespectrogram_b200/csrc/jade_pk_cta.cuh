@@ -138,6 +138,7 @@ JADE_KERNEL(32 * R1, PkCtaCfg<R1>::MINB) stft_pkcta_kernel(const KParams P)
     for (int i = t; i < P.npal; i += THREADS) s_pal[i] = P.palette[i];
     if (t == 0) mbar_init(bar, 1);
     __syncthreads();
+    grid_dep_wait();
 
     const unsigned total = (unsigned)P.ncols * (unsigned)P.nstreams;
     int ch0, ch1;
@@ -288,6 +289,7 @@ JADE_KERNEL(32 * R1, 1) stft_pkcta2_kernel(const KParams P)
     if (P.pooled)
         for (int i = t; i < P.R; i += THREADS) s_rows[i] = P.row_bins[i];
     __syncthreads();
+    grid_dep_wait();
 
     f2* se = reinterpret_cast<f2*>(P.scratch_e) + (long long)blockIdx.x * (M2 + 1);
     float* sp = P.scratch_p + (long long)blockIdx.x * (NH + 1);

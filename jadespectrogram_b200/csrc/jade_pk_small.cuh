@@ -84,6 +84,7 @@ JADE_KERNEL(PkSmallCfg<T>::WARPS * 32, JADE_PKS_CTAS) stft_pksmall_kernel(const 
     }
     for (int i = threadIdx.x; i < P.npal; i += blockDim.x) s_pal[i] = P.palette[i];
     __syncthreads();
+    grid_dep_wait();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int f = lane / T, s = lane % T;

@@ -94,6 +94,27 @@ def test_streaming_equals_batch(gpu_engine_factory):
     assert np.array_equal(sp, bpix[0])
 
 
+@pytest.mark.parametrize("N,ch", [(2048, 2), (2048, 1), (1024, 2), (4096, 1)])
+def test_streaming_pixels_only_equals_batch(gpu_engine_factory, N, ch):
+    """Pixel-only fetches take the polled completion path (armed ring slots, no event wait): same columns as the batch."""
+    hop, nblk = 512, 60
+    x = signals.streams(1, ch, hop * nblk, FS, kind="mix")
+    eng = gpu_engine_factory(sample_rate=FS, fft_size=N, hop=hop, channels=ch, ring_columns=64, max_push=512)
+    bpix, _ = eng.render_batch(x)
+    eng.reset()
+    cols, nxt = [], 0
+    for b in range(nblk):
+        eng.push(x[0][:, b * hop:(b + 1) * hop])
+        p, _, first = eng.fetch(max_cols=8, want_db=False)
+        if len(p):
+            assert first == nxt
+            nxt += len(p)
+            cols.extend(p)
+    sp = np.array(cols)
+    assert sp.shape[0] == eng.columns_for(hop * nblk)
+    assert np.array_equal(sp, bpix[0])
+
+
 def test_block_emit_mode_matches_reference_counts(gpu_engine_factory, oracle):
     """Reference emission pattern: feed 50 % -> 2 columns per N-sample block, newest column ends at (b+1)N - hop."""
     N = 1024
