@@ -125,7 +125,9 @@ int jade_log_rows(float fs, int fft_size, int rows, float fmin, float fmax, int3
 int jade_push_samples(jade_engine* e, const float* const* planar, int nch, int nsamples);
 /* Copies the columns produced since the previous fetch (oldest first, at most max_cols -- older ones are dropped
  * like the reference's ring overwrite) into pixels[ncols][rows] and, if not NULL, db[ncols][bins].  *first_col is
- * the absolute index of the first returned column.  Waits for the GPU work of earlier pushes. */
+ * the absolute index of the first returned column.  Returns when those columns are complete: pixel-only fetches of
+ * freshly pushed columns poll the pinned, device-mapped ring (no wait for kernel retirement), everything else waits for
+ * the GPU work of earlier pushes. */
 int jade_fetch_columns(jade_engine* e, uint32_t* pixels, float* db, int max_cols, int* ncols, int64_t* first_col);
 int jade_ring_info(jade_engine* e, int* ring_columns, int* rows, int* bins, int64_t* total_columns);
 /* Re-colour the whole ring from the stored dB values with the current palette/range (m_recomputeAll path,

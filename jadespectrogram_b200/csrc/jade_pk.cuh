@@ -188,7 +188,7 @@ JADE_DEVICE void win_stage1(f2* v, int j, f2 xa, f2 wa, f2 xb, f2 wb)
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// asynchronous global -> shared copy (LDGSTS) and the 64-bit lane shuffle
+// asynchronous global -> shared copy (LDGSTS; only the -DJADE_PK_LDGSTS experiment build uses it) and the 64-bit lane shuffle
 // ---------------------------------------------------------------------------------------------------------
 #if defined(JADE_EMU)
 inline void cp_async16(void* dst, const void* src) { std::memcpy(dst, src, 16); }
@@ -255,6 +255,7 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, int byte
 __device__ __forceinline__ void bulk_copy_issue(void* dst, const void* src, int bytes, unsigned long long* bar)
 {
     const unsigned d = (unsigned)__cvta_generic_to_shared(dst), b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // the issuing lane's own view, as in bulk_copy_g2s
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d), "l"(src),
                  "r"(bytes), "r"(b)
                  : "memory");
