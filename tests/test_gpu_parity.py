@@ -1,4 +1,6 @@
 """GPU parity tests: the CUDA path, called through the C ABI (libjade_gpu.so), against the CPU oracle."""
+import os
+
 import numpy as np
 import pytest
 
@@ -113,6 +115,39 @@ def test_streaming_pixels_only_equals_batch(gpu_engine_factory, N, ch):
     sp = np.array(cols)
     assert sp.shape[0] == eng.columns_for(hop * nblk)
     assert np.array_equal(sp, bpix[0])
+
+
+def _random_cases(n, seed=20241018):
+    rng = np.random.default_rng(seed)
+    cases = []
+    for _ in range(n):
+        N = int(rng.choice([128, 256, 512, 1024, 2048, 2048, 2048, 4096]))
+        hop = int(rng.choice([N // 8, N // 4, N // 2, N // 4 + 2, N // 4 + 1, int(rng.integers(16, N))]))
+        ch = int(rng.choice([1, 2, 2, 3, 4]))
+        mix = str(rng.choice(["absmean", "absmean", "absmean", "left", "right", "max"]))
+        ncols_total = int(rng.integers(12, 40))
+        extra = int(rng.integers(0, 7))          # odd lengths: 4-, 8- and unaligned sample counts
+        first = int(rng.integers(0, 6))
+        cases.append((N, hop, ch, mix, ncols_total, extra, first))
+    return cases
+
+
+@pytest.mark.parametrize("N,hop,ch,mix,ncols_total,extra,first", _random_cases(int(os.environ.get("JADE_RANDOM_CASES", "28"))))
+def test_random_geometries_match_oracle(gpu_engine_factory, oracle, N, hop, ch, mix, ncols_total, extra, first):
+    """Seeded random geometries: sizes, hops (aligned to 16, 8 bytes, or odd), channel counts / mixes, lengths and
+    column windows, so that every routing of launch_stft (staged, LDG, guarded, general) meets the oracle."""
+    n = hop * ncols_total + extra
+    x = signals.streams(2, ch, n, FS, kind="mix")
+    eng = gpu_engine_factory(sample_rate=FS, fft_size=N, hop=hop, channels=ch, window="hann", mix_mode=mix)
+    total = eng.columns_for(n)
+    ncols = max(1, min(total - first, ncols_total))
+    pix, db = eng.render_batch(x, first_col=first, ncols=ncols, want_db=True)
+    pix2, _ = eng.render_batch(x, first_col=first, ncols=ncols)
+    assert np.array_equal(pix, pix2)  # dB-storing and pixel-only instantiations agree
+    for s in range(2):
+        odb, opix = oracle.render_batch(x[s], fs=FS, fft_size=N, hop=hop, window="hann", mix=mix, first_col=first, ncols=ncols)
+        parity.check_db(db[s], odb, N, f"stream {s}")
+        parity.check_pixels(pix[s], opix, odb[:, ::-1], -50.0, 50.0, 256, f"stream {s}")
 
 
 def test_block_emit_mode_matches_reference_counts(gpu_engine_factory, oracle):
