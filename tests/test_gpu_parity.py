@@ -150,6 +150,34 @@ def test_random_geometries_match_oracle(gpu_engine_factory, oracle, N, hop, ch, 
         parity.check_pixels(pix[s], opix, odb[:, ::-1], -50.0, 50.0, 256, f"stream {s}")
 
 
+@pytest.mark.parametrize("seed,N,hop,ch", [(1, 2048, 512, 2), (2, 2048, 256, 1), (3, 1024, 512, 2), (4, 512, 128, 1),
+                                            (5, 4096, 1024, 2), (6, 2048, 510, 2), (7, 2048, 333, 1)])
+def test_streaming_random_pushes_equal_batch(gpu_engine_factory, seed, N, hop, ch):
+    """Pushes of random sizes (1 .. max_push samples: history slides, staging-slot reuse, columns appearing several at a
+    time), fetches alternating between the polled pixel-only path and the dB path: bit-identical to the batch render."""
+    rng = np.random.default_rng(seed)
+    n = hop * 90 + int(rng.integers(0, hop))
+    x = signals.streams(1, ch, n, FS, kind="mix")
+    eng = gpu_engine_factory(sample_rate=FS, fft_size=N, hop=hop, channels=ch, ring_columns=128, max_push=1500)
+    bpix, bdb = eng.render_batch(x, want_db=True)
+    eng.reset()
+    pos, nxt, k = 0, 0, 0
+    while pos < n:
+        m = int(min(n - pos, rng.integers(1, 1501)))
+        eng.push(x[0][:, pos:pos + m])
+        pos += m
+        want_db = (k % 3 == 2)
+        k += 1
+        p, d, first = eng.fetch(max_cols=64, want_db=want_db)
+        if len(p):
+            assert first == nxt
+            assert np.array_equal(p, bpix[0][nxt:nxt + len(p)])
+            if want_db:
+                assert np.array_equal(d, bdb[0][nxt:nxt + len(p)])
+            nxt += len(p)
+    assert nxt == eng.columns_for(n)
+
+
 def test_block_emit_mode_matches_reference_counts(gpu_engine_factory, oracle):
     """Reference emission pattern: feed 50 % -> 2 columns per N-sample block, newest column ends at (b+1)N - hop."""
     N = 1024
