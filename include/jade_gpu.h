@@ -19,6 +19,7 @@
  *   CColorPalette tables            (CColorpalette.cpp:100-339)  jade_palette_build, jade_set_palette
  *   CColorPalette::setValueRange    (CColorpalette.cpp:39-54)    jade_set_value_range
  *   getRGBColor | 0xFF000000 pixel loops (Spectrogram.cpp:623-724) fused into the kernels; jade_recolor_ring
+ *   timerCallback image assembly    (Spectrogram.cpp:590-724)    jade_view_*
  *   paint() crop maths              (Spectrogram.cpp:441-459)    jade_linear_crop, jade_config.row_map
  *   (offline batch rendering, north star)                        jade_render_batch / jade_render_device
  */
@@ -135,6 +136,20 @@ int jade_ring_info(jade_engine* e, int* ring_columns, int* rows, int* bins, int6
 int jade_recolor_ring(jade_engine* e, uint32_t* pixels);
 /* dB ring exactly as stored (slot order), db[ring_columns][bins]; unwritten slots hold -120 (Spectrogram.cpp:223) */
 int jade_read_ring_db(jade_engine* e, float* db);
+
+/* ---- display image (SpectrogramComponent::timerCallback, Spectrogram.cpp:590-724) ----
+ * Assembles the W x H ARGB32 image the component paints, with the reference's index rules: scroll mode (image shifted
+ * left, new columns on the right), fixed mode (columns at their ring position, red cursor at the write position) and the
+ * full redraw after a range / scheme change.  Colours come from the engine (pixel ring, jade_recolor_ring); the view only
+ * places columns.  It owns the engine's fetch cursor: do not mix with jade_fetch_columns on the same engine. */
+typedef struct jade_view jade_view;
+int jade_view_create(jade_engine* e, jade_view** out);
+int jade_view_destroy(jade_view* v);
+int jade_view_set_running(jade_view* v, int running);                     /* 1: scroll (default), 0: fixed + cursor */
+int jade_view_set_value_range(jade_view* v, float min_db, float max_db);  /* jade_set_value_range + full redraw */
+int jade_view_invalidate(jade_view* v);                                   /* m_recomputeAll = true */
+int jade_view_tick(jade_view* v, int* new_columns);                       /* one timerCallback; new_columns may be NULL */
+int jade_view_image(jade_view* v, const uint32_t** pixels, int* width, int* height); /* row-major [H][W], row 0 = top */
 
 /* ---- batch path ---- */
 /* number of columns the configured geometry yields for nsamples samples per channel */

@@ -70,6 +70,13 @@ SYMBOLS = {
     "jade_ring_info": (_I, [_P, _IP, _IP, _IP, C.POINTER(_I64)]),
     "jade_recolor_ring": (_I, [_P, _P]),
     "jade_read_ring_db": (_I, [_P, _P]),
+    "jade_view_create": (_I, [_P, _PP]),
+    "jade_view_destroy": (_I, [_P]),
+    "jade_view_set_running": (_I, [_P, _I]),
+    "jade_view_set_value_range": (_I, [_P, _F, _F]),
+    "jade_view_invalidate": (_I, [_P]),
+    "jade_view_tick": (_I, [_P, _IP]),
+    "jade_view_image": (_I, [_P, C.POINTER(C.POINTER(C.c_uint32)), _IP, _IP]),
     "jade_columns_for": (_I64, [_P, _I64]),
     "jade_render_batch": (_I, [_P, _P, _I, _I64, _I64, _I64, _P, _P]),
     "jade_render_batch_multi": (_I, [C.POINTER(_P), _I, _P, _I, _I64, _I64, _I64, _P, _P]),

@@ -1,0 +1,91 @@
+"""GPU test of the display-image assembly (jade_view_*, include/jade_gpu.h) against the restated
+SpectrogramComponent::timerCallback of the oracle (itself pinned bit for bit against the reference's real one,
+tests/test_oracle_vs_reference.py): scroll mode, fixed mode with the red cursor, full redraws after a range change."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import signals
+from jadespectrogram_b200 import Engine
+
+pytestmark = pytest.mark.gpu
+RED = 0xFFFF0000
+
+
+class View:
+    def __init__(self, eng):
+        self.eng, self.lib = eng, eng.lib
+        self.h = C.c_void_p()
+        assert self.lib.jade_view_create(eng.h, C.byref(self.h)) == 0
+
+    def tick(self):
+        n = C.c_int(0)
+        assert self.lib.jade_view_tick(self.h, C.byref(n)) == 0, self.lib.jade_last_error(self.eng.h)
+        return n.value
+
+    def image(self):
+        p, w, h = C.POINTER(C.c_uint32)(), C.c_int(0), C.c_int(0)
+        assert self.lib.jade_view_image(self.h, C.byref(p), C.byref(w), C.byref(h)) == 0
+        return np.ctypeslib.as_array(p, shape=(h.value, w.value)).copy()
+
+    def close(self):
+        self.lib.jade_view_destroy(self.h)
+
+
+def _compare(img, ref, table, label):
+    assert img.shape == ref.shape, (label, img.shape, ref.shape)
+    assert np.array_equal(img == RED, ref == RED), f"{label}: red cursor differs"
+    diff = img != ref
+    # colours come from float32 spectra that differ in the last bits: a few pixels may sit on the other side of a palette
+    # edge (tests/parity.py); they must be neighbours in the palette and rare
+    assert diff.mean() <= 2e-3, f"{label}: {diff.sum()} of {diff.size} pixels differ"
+    if diff.any():
+        index = {int(c) | 0xFF000000: i for i, c in reversed(list(enumerate(table)))}
+        a = np.array([index[int(c)] for c in img[diff]])
+        b = np.array([index[int(c)] for c in ref[diff]])
+        assert np.abs(a - b).max() <= 1, f"{label}: palette indices differ by {np.abs(a - b).max()}"
+
+
+@pytest.mark.parametrize("N,feed,ch", [(1024, "p50", 2), (2048, "p25", 1), (512, "p100", 2)])
+def test_view_follows_reference_timer_callback(N, feed, ch):
+    fs, mem_s = 48000.0, 0.5
+    pct = {"p100": 100, "p50": 50, "p25": 25, "p10": 10}[feed]
+    eng = Engine(0, sample_rate=fs, fft_size=N, channels=ch, feed_percent=pct, memory_time_s=mem_s, max_push=N)
+    eng.set_palette_scheme("jade", 256)
+    eng.set_value_range(-50.0, 50.0)
+    spec, pal = O.Spec(), O.Palette(256, O.PAL["jade"])
+    spec.set_channels(ch)
+    spec.set_samplerate(fs)
+    spec.set_memory_time_s(mem_s)
+    spec.set_fftsize(N)
+    spec.set_feed_percent(O.FEED[feed])
+    table = pal.table()
+    ov, gv = O.View(spec, pal), View(eng)
+    W = spec.memory_size()
+    nblocks = 3 * W // spec.feed_blocks() + 5  # wraps the ring several times
+    x = signals.streams(1, ch, N * nblocks, fs, kind="mix")[0]
+    x *= 20.0
+    ticks = 0
+    for b in range(nblocks):
+        blk = x[:, b * N:(b + 1) * N]
+        eng.push(blk)
+        spec.process(blk)
+        if b == nblocks // 3:          # the "Fix" button: fixed mode with the red cursor
+            ov.set_running(False)
+            assert eng.lib.jade_view_set_running(gv.h, 0) == 0
+        if b == nblocks // 2:          # a range slider moves: full redraw
+            ov.set_color_range(-70.0, 20.0)
+            assert eng.lib.jade_view_set_value_range(gv.h, -70.0, 20.0) == 0
+        if b == (2 * nblocks) // 3:    # back to scrolling
+            ov.set_running(True)
+            assert eng.lib.jade_view_set_running(gv.h, 1) == 0
+        if b % 3 == 1 or b == nblocks - 1:
+            no, ng = ov.tick(), gv.tick()
+            assert no == ng, (b, no, ng)
+            _compare(gv.image(), ov.image(), table, f"block {b}")
+            ticks += 1
+    assert ticks > 6
+    gv.close()
+    eng.close()
