@@ -365,7 +365,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--streams", type=int, default=256, help="streams per GPU per step")
-    ap.add_argument("--e2e-streams", type=int, default=64)
+    ap.add_argument("--e2e-streams", type=int, default=128)
     ap.add_argument("--latency-blocks", type=int, default=2000)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
