@@ -5,10 +5,12 @@ Workload (config.workload = "cfg2-batch"): BASELINE configs[1] geometry -- stere
 AbsMean mix, dB, Jade/256 palette over -50..+50 dB, one ARGB32 pixel per bin (1025 rows) -- applied to a batch of
 independent synthetic streams (noise*0.1 + sine sweep).  A "step" is one pass of the hot path over that batch.
 
-  value   : frames/s with the inputs already resident in HBM (one kernel launch per step, CUDA events, max over ranks)
+  value   : frames/s with the inputs already resident in HBM (one main kernel launch + one for the boundary columns per
+            step, CUDA events, max over ranks)
   e2e     : frames/s through the reference-facing C ABI call jade_render_batch with pinned HOST buffers
             (H2D of the samples and D2H of the pixel columns inside the timed region)
-  latency : per-block time of the real-time path (512-sample blocks, push + fetch through the C ABI)
+  latency : per-block time of the real-time path (512-sample blocks, push + fetch through the C ABI, from a native C++
+            caller -- tools/native/latency_probe -- with the Python loop's numbers beside it)
   roofline: algorithmic bytes (4*hop*C + 4*R per frame) / kernel time against the measured HBM copy bandwidth
   cpu_baseline: the CPU oracle port timed on this box's host cores on a bounded sample
 
