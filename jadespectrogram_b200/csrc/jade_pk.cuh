@@ -1,7 +1,7 @@
 // jade_pk.cuh -- the headline kernel: N = 2048 (BASELINE configs[1] / [3]) with packed FP32x2 arithmetic.
 //
 // Same fused path as jade_kernels.cuh (framing, window, real FFT, |X|^2, channel mix, dB, flip, palette, packed pixel
-// store; reference lines cited there), restructured around what limits it on sm_100a (profiles/r01*, r02*):
+// store; reference lines cited there), restructured around what limits it on sm_100a (profiles/r01*, r01_s2_*):
 //   * every complex value lives in ONE 64-bit register pair and all butterflies / twiddle products are FFMA2 / FADD2 /
 //     FMUL2 (PTX fma/add/mul.rn.f32x2): a complex add is 1 instruction, a complex multiply 2, a general radix-2
 //     butterfly 3 (a' = a + W b by two chained FFMA2, b' = 2a - a').  ptxas folds the half-swap, the per-half sign
@@ -21,7 +21,7 @@
 //     that they are read with conflict-free LDS.128 (two table entries per instruction); the transpose rows are 16-byte
 //     aligned for the same reason.
 //   * 12 warps per SM with up to 168 registers each (one CTA per SM): the 16-warp / 128-register shape spills the stereo
-//     accumulators and is 12 % slower; 8 warps lose 8 % (profiles/r02_pk2048_variants.txt).
+//     accumulators and is 12 % slower; 8 warps lose 8 % (profiles/r01_s2_pk2048_variants.txt).
 //
 // One warp transforms one frame: M = 1024 complex points z[m] = x[2m] + i x[2m+1], 32 per lane (m = s + 32 n1), radix-32
 // in registers, one transpose through shared memory, twisted radix-32 in registers: lane s ends with Z[s + 32 k2].
@@ -674,7 +674,7 @@ JADE_KERNEL(PkCfg::WARPS * 32, JADE_PK_CTAS) stft_pk2048_kernel(const KParams P)
 // ---------------------------------------------------------------------------------------------------------
 // Stereo kernel (AbsMean over exactly two channels, the BASELINE configs[1] shape): one warp transforms BOTH channels of a
 // frame at once, so that every window, twiddle and split-twiddle value is read from shared memory once for the two
-// (the shared-memory pipe is the limiter, profiles/r02_pk2048_stereo.txt: the tables are 256 of 813 wavefronts per stereo
+// (the shared-memory pipe is the limiter, profiles/r01_s2_pk2048_stereo.txt: the tables are 256 of 813 wavefronts per stereo
 // frame), the two powers add up without accumulators living through a transform, and the two independent dependency
 // chains give the scheduler extra parallelism.  12 warps per SM, <= 168 registers.  Interior, 16-byte aligned frames only
 // (TMA staging as in PK_LD_ASYNC, one mbarrier completion for the two 8 KB copies); everything else goes to
