@@ -7,9 +7,12 @@
 //   pass 1 : radix-32 over n1 in registers (window fused into stage 1), twiddle W_M^(s k1);
 //   transpose inside the frame's T lanes through a padded shared-memory tile (32 rows of T+1);
 //   pass 2 : lane s owns rows k1 = s + T i (i < F) and runs F radix-T DFTs: u[i T + k2] = Z[(s + T i) + 32 k2];
-//   split  : pairs (k, M-k) with k2 < T/2: pair q = i T/2 + k2 of lane s has its partner in lane T - s, and the
-//            exchange tile is laid out so that it sits in row 15 - q, column T - s for EVERY lane: lane 0 (whose partners
-//            are its own values at irregular indices) files them into the extra column T itself;
+//   split  : pairs (k, M-k) with k2 < T/2: pair q = i T/2 + k2 of lane s has its partner in register (F-1-i) T + (T-1-k2)
+//            of lane T - s of the same frame and receives it by SHFL.IDX (nothing goes through shared memory; the smem
+//            exchange tile it replaces cost 32 wavefronts per warp more and two more barriers); lane s = 0, whose
+//            partners are its own values at irregular indices (lane0_partner), selects them instead;
+//   staging: the F frames (8 KB) a warp transforms next are copied into its tiles by the TMA engine right after the
+//            transpose has been read back (cp.async.bulk, one mbarrier per warp);
 //   epilogue as in jade_pk.cuh.
 // Same reference lines replaced as jade_kernels.cuh (Spectrogram.cpp:50-56,137-145,64-107,634-647; CColorpalette.h:32-47).
 #pragma once
@@ -33,7 +36,7 @@ struct PkSmallCfg {
     static constexpr int WARPS = JADE_PKS_WARPS;
     static constexpr int ROW = 34;    // f2 words per s-row of the window / inter-pass twiddle tables (32 + 16 B pad)
     static constexpr int PROW = 18;   // f2 words per s-row of the split-twiddle table (16 + 16 B pad)
-    // per-frame tile (f2 words): 32 rows of T+1 for the transpose, reused as 16 rows of T+1 for the exchange; the stride
+    // per-frame tile (f2 words): 32 rows of T+1 for the transpose (and the landing area of the next frame); the stride
     // between the F tiles of a warp is kept == T (mod 16) so that frames sharing a half-warp hit disjoint banks
     static constexpr int FS = 32 * (T + 1) + (T < 16 ? T : 0);
     static constexpr int off_win = 0;
@@ -94,8 +97,7 @@ JADE_KERNEL(PkSmallCfg<T>::WARPS * 32, JADE_PKS_CTAS) stft_pksmall_kernel(const 
     const f2x2* prow = reinterpret_cast<const f2x2*>(s_twP + s * Cfg::PROW);
     f2* tr_wr = xw + s;               // transpose: word k1*TS + s
     const f2* tr_rd = xw + s * TS;    //            row k1 = s + T i at tr_rd[T*i*TS + j]
-    f2* ex_wr = xw + s;               // exchange: row r(i', k2') = i' H + (k2' - H), word r*TS + s   (k2' >= H)
-    const f2* ex_rd = xw + (T - s);   // partner of pair q: row 15 - q, column T - s (lane 0: the extra column T)
+    const int plane = (lane & ~(T - 1)) | ((T - s) & (T - 1)); // lane of the same frame holding the mirrored bins
 
     const unsigned groups = (unsigned)((P.ncols + F - 1) / F);
     const unsigned total = groups * (unsigned)P.nstreams;
@@ -191,28 +193,18 @@ JADE_KERNEL(PkSmallCfg<T>::WARPS * 32, JADE_PKS_CTAS) stft_pksmall_kernel(const 
                 for (int jx = 0; jx < T; ++jx) u[i * T + brev(jx, ilog2c(T))] = tr_rd[T * i * TS + jx];
                 fft_pk<T>(u + i * T); // u[i T + k2] = Z[(s + T i) + 32 k2]
             }
-            __syncwarp();
-#pragma unroll
-            for (int i = 0; i < F; ++i)
-#pragma unroll
-                for (int k2 = H; k2 < T; ++k2) ex_wr[(i * H + (k2 - H)) * TS] = u[i * T + k2];
-            if (s == 0) { // lane 0 pairs with itself: file its partners into the extra column T (word r*TS + T)
-#pragma unroll
-                for (int q = 0; q < 16; ++q) xw[(15 - q) * TS + T] = u[lane0_partner<T>(q)];
-            }
-            __syncwarp();
-            f2 zpv[16];
-#pragma unroll
-            for (int q = 0; q < 16; ++q) zpv[q] = ex_rd[(15 - q) * TS];
             __syncwarp(); // the tiles are free again
             if (!GUARD) { // stage what this warp transforms next: the next channel of this group, or its next group
                 if (ch + 1 < ch1) stage(g, ch + 1);
                 else if (g + gstep < total) stage(g + gstep, ch0);
             }
+            // Pair split.  Z[M - k] of pair q = i H + k2 (k = s + T i + 32 k2) is register (F-1-i) T + (T-1-k2) of lane
+            // T - s of the same frame and arrives by SHFL.IDX; lane s = 0 pairs with its own lane0_partner<T>(q).
 #pragma unroll
             for (int q = 0; q < 16; ++q) {
-                const int uq = (q / H) * T + (q % H);
-                const f2 zp = zpv[q];
+                const int iq = q / H, k2 = q % H;
+                const int uq = iq * T + k2;
+                const f2 zp = sel2(s == 0, u[lane0_partner<T>(q)], shfl2(u[(F - 1 - iq) * T + (T - 1 - k2)], plane));
                 const f2x2 wq = prow[q / 2];
                 const f2 A = add2(u[uq], conj2(zp));  // Z[k] + conj Z[M-k]
                 const f2 Bv = sub2(u[uq], conj2(zp)); // Z[k] - conj Z[M-k]
