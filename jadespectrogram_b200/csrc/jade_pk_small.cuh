@@ -4,9 +4,11 @@
 //
 // T lanes transform one frame (F = 32 / T frames per warp), M = 32 T complex points z[m] = x[2m] + i x[2m+1], 32 per lane
 // (m = s + T n1, s = lane % T):
-//   pass 1 : radix-32 over n1 in registers (window fused into stage 1), twiddle W_M^(s k1);
+//   pass 1 : radix-32 over n1 in registers (window fused into stage 1);
 //   transpose inside the frame's T lanes through a padded shared-memory tile (32 rows of T+1);
-//   pass 2 : lane s owns rows k1 = s + T i (i < F) and runs F radix-T DFTs: u[i T + k2] = Z[(s + T i) + 32 k2];
+//   pass 2 : lane s owns rows k1 = s + T i (i < F) and runs F twisted radix-T DFTs whose butterflies carry the inter-pass
+//            twiddle W_M^(k1 j) (fft_twisted: 16 table values per lane instead of 31 and no twiddle multiply):
+//            u[i T + k2] = Z[(s + T i) + 32 k2];
 //   split  : pairs (k, M-k) with k2 < T/2: pair q = i T/2 + k2 of lane s has its partner in register (F-1-i) T + (T-1-k2)
 //            of lane T - s of the same frame and receives it by SHFL.IDX (nothing goes through shared memory; the smem
 //            exchange tile it replaces cost 32 wavefronts per warp more and two more barriers); lane s = 0, whose
@@ -27,6 +29,50 @@
 #endif
 
 namespace jade {
+
+// Twisted R-point DIT pass (R = 2 .. 16), the small sibling of fft32_twisted (jade_pk.cuh): the inter-pass twiddle
+// W_M^{k1 j} of row k1 rides in the butterflies, stage LEN uses W_M^{(R/LEN)(k1 + 32 J)} (M = 32 R), J < LEN/2, and
+// J >= LEN/4 is -i times entry J - LEN/4: R/2 table values per row at tw[0] (LEN 2), tw[1] (LEN 4), tw[2..3] (LEN 8),
+// tw[4..7] (LEN 16).  Bit-reversed input, natural-order output.
+template <int R, int LEN, int BASE, int J>
+JADE_DEVICE void twr_inner(f2* a, const f2* tw)
+{
+    if constexpr (J < LEN / 2) {
+        constexpr int Q = (LEN >= 4) ? LEN / 4 : 1;
+        if constexpr (J < Q) bfly_w(a[BASE + J], a[BASE + J + LEN / 2], tw[J]);
+        else bfly_wmi(a[BASE + J], a[BASE + J + LEN / 2], tw[J - Q]);
+        twr_inner<R, LEN, BASE, J + 1>(a, tw);
+    }
+}
+template <int R, int LEN, int BASE>
+JADE_DEVICE void twr_blocks(f2* a, const f2* tw)
+{
+    if constexpr (BASE < R) {
+        twr_inner<R, LEN, BASE, 0>(a, tw);
+        twr_blocks<R, LEN, BASE + LEN>(a, tw);
+    }
+}
+template <int R, int LEN>
+JADE_DEVICE void twr_stages(f2* a, const f2* tw)
+{
+    if constexpr (LEN <= R) {
+        twr_blocks<R, LEN, 0>(a, tw + (LEN >= 4 ? LEN / 4 : 0));
+        twr_stages<R, LEN * 2>(a, tw);
+    }
+}
+template <int R>
+JADE_DEVICE void fft_twisted(f2* a, const f2* tw)
+{
+    twr_stages<R, 2>(a, tw);
+}
+// exponent e (entry = W_M^e, M = 32 R) of table value t (0 .. R/2-1) of row k1
+template <int R>
+JADE_HD int twr_exponent(int k1, int t)
+{
+    const int LEN = t == 0 ? 2 : (t == 1 ? 4 : (t < 4 ? 8 : 16));
+    const int J = t < 2 ? 0 : t - LEN / 4;
+    return (R / LEN) * (k1 + 32 * J);
+}
 
 template <int T>
 struct PkSmallCfg {
@@ -77,8 +123,11 @@ JADE_KERNEL(PkSmallCfg<T>::WARPS * 32, JADE_PKS_CTAS) stft_pksmall_kernel(const 
     for (int i = threadIdx.x; i < M; i += blockDim.x) {
         const int s = i % T, n1 = i / T;                         // m = s + T n1
         s_win[s * Cfg::ROW + n1] = pk(P.window[2 * i], P.window[2 * i + 1]);
-        const cpx t = P.twI[n1 * T + s];                         // W_M^(k1 s), k1 = n1 here
-        s_twI[s * Cfg::ROW + n1] = pk(t.x, t.y);
+    }
+    for (int i = threadIdx.x; i < 16 * T; i += blockDim.x) { // twisted pass-2 table: [s][ip (T/2) + t] for row k1 = s + T ip
+        const int s = i % T, q = i / T, ip = q / H, t = q % H;
+        const cpx w = P.twP[2 * twr_exponent<T>(s + T * ip, t)]; // W_M^e = W_N^{2e}
+        s_twI[s * Cfg::ROW + q] = pk(w.x, w.y);
     }
     for (int i = threadIdx.x; i < 16 * T; i += blockDim.x) {
         const int s = i % T, q = i / T;                          // pair q = ip H + k2: k = s + T ip + 32 k2
@@ -180,18 +229,20 @@ JADE_KERNEL(PkSmallCfg<T>::WARPS * 32, JADE_PKS_CTAS) stft_pksmall_kernel(const 
             if (!GUARD) __syncwarp(); // every lane has read its samples before the transpose overwrites them
             fft32_pk_after_stage1(v);
 #pragma unroll
-            for (int k1 = 0; k1 < 32; k1 += 2) {
-                const f2x2 t = trow[k1 / 2];
-                tr_wr[k1 * TS] = (k1 == 0) ? v[0] : cmul2(v[k1], t.a);
-                tr_wr[(k1 + 1) * TS] = cmul2(v[k1 + 1], t.b);
-            }
+            for (int k1 = 0; k1 < 32; ++k1) tr_wr[k1 * TS] = v[k1];
             __syncwarp();
-            f2 u[32];
+            f2 u[32], twl[16]; // this lane's 16 twisted twiddles: T/2 per row
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const f2x2 t = trow[i];
+                twl[2 * i] = t.a;
+                twl[2 * i + 1] = t.b;
+            }
 #pragma unroll
             for (int i = 0; i < F; ++i) {
 #pragma unroll
                 for (int jx = 0; jx < T; ++jx) u[i * T + brev(jx, ilog2c(T))] = tr_rd[T * i * TS + jx];
-                fft_pk<T>(u + i * T); // u[i T + k2] = Z[(s + T i) + 32 k2]
+                fft_twisted<T>(u + i * T, twl + i * H); // u[i T + k2] = Z[(s + T i) + 32 k2], twiddle W_M^(k1 j) included
             }
             __syncwarp(); // the tiles are free again
             if (!GUARD) { // stage what this warp transforms next: the next channel of this group, or its next group
