@@ -201,7 +201,14 @@ int choose_kernel(jade_engine* e)
         // fast path: packed-FP32x2 kernels (jade_pk.cuh for N = 2048, jade_pk_small.cuh below)
         const int T = N / 64;
         kc.family = 3;
-        const int warps = (T == 32) ? jade::PkCfg::WARPS : jade::PkSmallCfg<2>::WARPS;
+        int warps = jade::PkCfg::WARPS;
+        switch (T) {
+        case 2: warps = jade::PkSmallCfg<2>::WARPS; break;
+        case 4: warps = jade::PkSmallCfg<4>::WARPS; break;
+        case 8: warps = jade::PkSmallCfg<8>::WARPS; break;
+        case 16: warps = jade::PkSmallCfg<16>::WARPS; break;
+        default: break;
+        }
         kc.threads = warps * 32;
         kc.units_per_block = warps * (32 / T);
         switch (T) {

@@ -20,14 +20,9 @@
 #pragma once
 #include "jade_pk.cuh"
 
-// occupancy: JADE_PKS_WARPS warps per CTA, JADE_PKS_CTAS CTAs per SM
-#ifndef JADE_PKS_WARPS
-#define JADE_PKS_WARPS 8
-#endif
-#ifndef JADE_PKS_CTAS
-#define JADE_PKS_CTAS 2
-#endif
-
+// occupancy: T >= 8 (N = 512, 1024): 12 warps per SM with up to 168 registers (one CTA); smaller T: 16 warps of 128
+// registers (two CTAs of 8) -- measured both ways for every T (gpurun_out: 12 x 1 is +6 % at N = 1024, -7 % at N = 128).
+// -DJADE_PKS_WARPS / -DJADE_PKS_CTAS override both for experiments.
 namespace jade {
 
 // Twisted R-point DIT pass (R = 2 .. 16), the small sibling of fft32_twisted (jade_pk.cuh): the inter-pass twiddle
@@ -79,7 +74,11 @@ struct PkSmallCfg {
     static constexpr int M = 32 * T, N = 2 * M, B = M + 1;
     static constexpr int F = 32 / T;
     static constexpr int H = T / 2;   // k2 values per pair half
-    static constexpr int WARPS = JADE_PKS_WARPS;
+#if defined(JADE_PKS_WARPS) && defined(JADE_PKS_CTAS)
+    static constexpr int WARPS = JADE_PKS_WARPS, CTAS = JADE_PKS_CTAS;
+#else
+    static constexpr int WARPS = (T >= 8) ? 12 : 8, CTAS = (T >= 8) ? 1 : 2;
+#endif
     static constexpr int ROW = 34;    // f2 words per s-row of the window / inter-pass twiddle tables (32 + 16 B pad)
     static constexpr int PROW = 18;   // f2 words per s-row of the split-twiddle table (16 + 16 B pad)
     // per-frame tile (f2 words): 32 rows of T+1 for the transpose (and the landing area of the next frame); the stride
@@ -104,7 +103,7 @@ JADE_HD constexpr int lane0_partner(int q)
 }
 
 template <int T, int MIXK, bool WANT_DB, bool GUARD>
-JADE_KERNEL(PkSmallCfg<T>::WARPS * 32, JADE_PKS_CTAS) stft_pksmall_kernel(const KParams P)
+JADE_KERNEL(PkSmallCfg<T>::WARPS * 32, PkSmallCfg<T>::CTAS) stft_pksmall_kernel(const KParams P)
 {
     using Cfg = PkSmallCfg<T>;
     constexpr int M = Cfg::M, F = Cfg::F, H = Cfg::H, FS = Cfg::FS, TS = T + 1;

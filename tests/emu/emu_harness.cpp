@@ -45,7 +45,7 @@ void run_cta(const KParams& P, int mixk, bool general, int grid)
 template <int T, int MIXK, bool WDB, bool GUARD>
 void run_pk_one(const KParams& P, int npal, int grid)
 {
-    const int block = (T == 32 ? jade::PkCfg::WARPS : jade::PkSmallCfg<2>::WARPS) * 32;
+    const int block = (T == 32 ? jade::PkCfg::WARPS : jade::PkSmallCfg<(T == 32 ? 16 : T)>::WARPS) * 32;
     if constexpr (T == 32) {
         // same routing as launch_stft: guard / cp.async staging (16-byte aligned) / LDG to registers (8-byte aligned)
         // stereo kernel for AbsMean over two channels unless JADE_EMU_NOPAIR is set (tests cover both)
