@@ -158,7 +158,11 @@ JADE_DEVICE uint32_t colour_of_lg(float lg, const KParams& P, const uint32_t* pa
     int idx = (int)fm(lg, P.ck1, P.ck0);
     idx = max(min(idx, P.npal - 1), 0);
     idx = (lg >= P.clg_hi) ? P.ci_hi : idx;
+#if defined(JADE_ABL_NOPAL)
+    return (uint32_t)idx;
+#else
     return pal[idx];
+#endif
 }
 // host side: fill ck1, ck0, clg_hi, ci_hi from pmin, pmax, pmaxc, pmult, npal
 inline void colour_fold(KParams& P)
@@ -176,6 +180,12 @@ inline void colour_fold(KParams& P)
 template <int MIXK, bool WANT_DB>
 JADE_DEVICE void emit_bin(float p, float scale, uint32_t* pix, float* db, const KParams& P, const uint32_t* pal)
 {
+#if defined(JADE_ABL_NOEPI)
+    if (!WANT_DB) {
+        *pix = (uint32_t)(int)fm(p, scale, 1e-11f);
+        return;
+    }
+#endif
     const float lg = JADE_LOG2F(MIXK == 1 /* MIX_SUM */ ? fm(p, scale, 1e-11f) : JADE_FADD(p, 1e-11f));
     if (WANT_DB) {
         if (db) *db = JADE_FMUL(3.01029995663981195f, lg);

@@ -391,29 +391,34 @@ JADE_DEVICE void tw32_half2(f2* ua, f2* ub, const f2x2 ta, const f2x2 tb)
         bfly_wmi(ub[J0 + i + 8], ub[J0 + i + 24], w[i]);
     }
 }
+#if defined(JADE_ABL_NOTW)
+#define JADE_TROW(i) trow[0]
+#else
+#define JADE_TROW(i) trow[i]
+#endif
 JADE_DEVICE void fft32_twisted2(f2* ua, f2* ub, const f2x2* trow)
 {
     {
-        const f2x2 t = trow[0];
+        const f2x2 t = JADE_TROW(0);
         tw_blocks<2, 0>(ua, &t.a);
         tw_blocks<2, 0>(ub, &t.a);
         tw_blocks<4, 0>(ua, &t.b);
         tw_blocks<4, 0>(ub, &t.b);
     }
     {
-        const f2x2 t = trow[1];
+        const f2x2 t = JADE_TROW(1);
         const f2 w[2] = {t.a, t.b};
         tw_blocks<8, 0>(ua, w);
         tw_blocks<8, 0>(ub, w);
     }
     {
-        const f2x2 t0 = trow[2], t1 = trow[3];
+        const f2x2 t0 = JADE_TROW(2), t1 = JADE_TROW(3);
         const f2 w[4] = {t0.a, t0.b, t1.a, t1.b};
         tw_blocks<16, 0>(ua, w);
         tw_blocks<16, 0>(ub, w);
     }
-    tw32_half2<0>(ua, ub, trow[4], trow[5]);
-    tw32_half2<4>(ua, ub, trow[6], trow[7]);
+    tw32_half2<0>(ua, ub, JADE_TROW(4), JADE_TROW(5));
+    tw32_half2<4>(ua, ub, JADE_TROW(6), JADE_TROW(7));
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -753,28 +758,49 @@ JADE_KERNEL(PkPairCfg::WARPS * 32, 1) stft_pk2048x2_kernel(const KParams P)
         const ColOut o = col_out(P, un.stream, un.j);
 
         f2 va[32], vb[32];
+#if defined(JADE_ABL_NOSTAGE)
+        if (copies == 0)
+#endif
         mbar_wait(bar, copies & 1u);
         ++copies;
 #pragma unroll
         for (int jj = 0; jj < 16; jj += 2) {
+#if defined(JADE_ABL_NOWIN)
+            const f2x2 wa = wrow[0], wb = wrow[1];
+#else
             const f2x2 wa = wrow[jj / 2], wb = wrow[(jj + 16) / 2];
+#endif
             const f2* za = xa + s;
             const f2* zb = xb + s;
-            win_stage1(va, jj, za[32 * jj], wa.a, za[32 * (jj + 16)], wb.a);
-            win_stage1(va, jj + 1, za[32 * (jj + 1)], wa.b, za[32 * (jj + 17)], wb.b);
-            win_stage1(vb, jj, zb[32 * jj], wa.a, zb[32 * (jj + 16)], wb.a);
-            win_stage1(vb, jj + 1, zb[32 * (jj + 1)], wa.b, zb[32 * (jj + 17)], wb.b);
+#if defined(JADE_ABL_NOLOAD)
+#define ABL_LD(z, i) z[32 * ((i) & 1)]
+#else
+#define ABL_LD(z, i) z[32 * (i)]
+#endif
+            win_stage1(va, jj, ABL_LD(za, jj), wa.a, ABL_LD(za, jj + 16), wb.a);
+            win_stage1(va, jj + 1, ABL_LD(za, jj + 1), wa.b, ABL_LD(za, jj + 17), wb.b);
+            win_stage1(vb, jj, ABL_LD(zb, jj), wa.a, ABL_LD(zb, jj + 16), wb.a);
+            win_stage1(vb, jj + 1, ABL_LD(zb, jj + 1), wa.b, ABL_LD(zb, jj + 17), wb.b);
         }
         __syncwarp(); // every lane has read its samples before the transposes overwrite them
+#if !defined(JADE_ABL_NOFP1)
         fft32_pk_after_stage1(va);
         fft32_pk_after_stage1(vb);
+#endif
+        f2 ua[32], ub[32];
+#if defined(JADE_ABL_NOXPOSE)
+#pragma unroll
+        for (int k1 = 0; k1 < 32; ++k1) {
+            ua[k1] = va[k1];
+            ub[k1] = vb[k1];
+        }
+#else
 #pragma unroll
         for (int k1 = 0; k1 < 32; ++k1) {
             xa[k1 * Cfg::XROW + s] = va[k1];
             xb[k1 * Cfg::XROW + s] = vb[k1];
         }
         __syncwarp();
-        f2 ua[32], ub[32];
         {
             const f2x2* ra = reinterpret_cast<const f2x2*>(xa + s * Cfg::XROW);
             const f2x2* rb = reinterpret_cast<const f2x2*>(xb + s * Cfg::XROW);
@@ -787,9 +813,14 @@ JADE_KERNEL(PkPairCfg::WARPS * 32, 1) stft_pk2048x2_kernel(const KParams P)
                 ub[brev(jx + 1, 5)] = tb.b;
             }
         }
+#endif
         __syncwarp(); // the buffers are free again
+#if !defined(JADE_ABL_NOSTAGE)
         if (g + gstep < total) stage(g + gstep); // stage the next frame of this warp
+#endif
+#if !defined(JADE_ABL_NOFP2)
         fft32_twisted2(ua, ub, trow);
+#endif
 
         uint32_t* p_lo = o.pix ? o.pix + (M - s) : nullptr; // bin k -> row M - k
         uint32_t* p_hi = o.pix ? o.pix + s : nullptr;
@@ -797,9 +828,17 @@ JADE_KERNEL(PkPairCfg::WARPS * 32, 1) stft_pk2048x2_kernel(const KParams P)
         float* d_hi = (WANT_DB && o.db) ? o.db + (M - s) : nullptr;
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
+#if defined(JADE_ABL_NOSHFL)
+            const f2 zpa = ua[31 - q], zpb = ub[31 - q];
+#else
             const f2 zpa = sel2(s == 0, ua[(32 - q) & 31], shfl2(ua[31 - q], partner));
             const f2 zpb = sel2(s == 0, ub[(32 - q) & 31], shfl2(ub[31 - q], partner));
+#endif
+#if defined(JADE_ABL_NOTW)
+            const f2x2 wq2 = prow[0];
+#else
             const f2x2 wq2 = prow[q / 2];
+#endif
             const f2 wq = (q & 1) ? wq2.b : wq2.a;
             const f2 Aa = add2(ua[q], conj2(zpa)), Ba = sub2(ua[q], conj2(zpa));
             const f2 Ab = add2(ub[q], conj2(zpb)), Bb = sub2(ub[q], conj2(zpb));

@@ -76,18 +76,29 @@ public:
             out[1] = O(b * b);
             return;
         }
-        for (size_t i = 0; i < h; ++i) m_work[m_rev[i]] = std::complex<T>(T(in[2 * i]), T(in[2 * i + 1]));
+        /* Raw interleaved (re, im) arrays instead of std::complex element access: the same operations in the same order
+         * (bit-identical results), but the loops compile to straight scalar code (about 10x faster at -O2), so that the
+         * CPU baseline timed through this stand-in is not handicapped by the container class. */
+        T* __restrict w = reinterpret_cast<T*>(m_work.data());
+        const T* __restrict tw = reinterpret_cast<const T*>(m_tw.data());
+        for (size_t i = 0; i < h; ++i) {
+            w[2 * m_rev[i]] = T(in[2 * i]);
+            w[2 * m_rev[i] + 1] = T(in[2 * i + 1]);
+        }
         for (size_t len = 2; len <= h; len <<= 1) {
-            const size_t step = h / len;
+            const size_t step = h / len, half = len / 2;
             for (size_t base = 0; base < h; base += len) {
-                for (size_t j = 0; j < len / 2; ++j) {
-                    const std::complex<T> w = m_tw[j * step];
-                    const std::complex<T> a = m_work[base + j];
-                    const std::complex<T> b = m_work[base + j + len / 2];
-                    const T tr = w.real() * b.real() - w.imag() * b.imag();
-                    const T ti = w.real() * b.imag() + w.imag() * b.real();
-                    m_work[base + j] = std::complex<T>(a.real() + tr, a.imag() + ti);
-                    m_work[base + j + len / 2] = std::complex<T>(a.real() - tr, a.imag() - ti);
+                T* __restrict pa = w + 2 * base;
+                T* __restrict pb = w + 2 * (base + half);
+                for (size_t j = 0; j < half; ++j) {
+                    const T wr = tw[2 * j * step], wi = tw[2 * j * step + 1];
+                    const T ar = pa[2 * j], ai = pa[2 * j + 1], br = pb[2 * j], bi = pb[2 * j + 1];
+                    const T tr = wr * br - wi * bi;
+                    const T ti = wr * bi + wi * br;
+                    pa[2 * j] = ar + tr;
+                    pa[2 * j + 1] = ai + ti;
+                    pb[2 * j] = ar - tr;
+                    pb[2 * j + 1] = ai - ti;
                 }
             }
         }
@@ -583,16 +594,20 @@ int jo_window(int window, int n, float* out)
     std::copy(w.begin(), w.end(), out);
     return 0;
 }
+/* The plan (twiddles, split table, bit reversal) is kept per thread and rebuilt only when n changes, as any plan-caching
+ * FFT class would between setFFTSize calls (Spectrogram.cpp:215); results are bit-identical to a fresh plan. */
 int jo_power_f32(const float* x, int n, float* power)
 {
-    RealFftPower<float> f(n);
+    static thread_local RealFftPower<float> f;
+    f.setFFTSize(size_t(n));
     if (!f.valid()) return -1;
     f.power(x, power);
     return 0;
 }
 int jo_power_f64(const float* x, int n, double* power)
 {
-    RealFftPower<double> f(n);
+    static thread_local RealFftPower<double> f;
+    f.setFFTSize(size_t(n));
     if (!f.valid()) return -1;
     f.power(x, power);
     return 0;

@@ -1,6 +1,8 @@
 /* Stand-in for the author's TGM "FFT.h" (class spectrum), which is NOT in /root/reference and has no pinned version
  * (PARITY UNPINNED, see oracle/jade_oracle.h).  Forwards to the oracle's float32 FFT so that the compiled reference
- * and the restated oracle use the very same FFT and can be compared bit for bit.  TEST INFRASTRUCTURE ONLY. */
+ * and the restated oracle use the very same FFT and can be compared bit for bit.  jo_power_f32 keeps its plan per thread and
+ * per size (rebuilt only when the size changes, as after setFFTSize, Spectrogram.cpp:215), so timing the compiled reference
+ * through this shim does not pay for re-planning on every frame.  TEST INFRASTRUCTURE ONLY. */
 #pragma once
 #include <cstddef>
 #include <vector>
