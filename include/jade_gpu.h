@@ -110,6 +110,10 @@ int jade_reset(jade_engine* e);                           /* buildmem() without 
 /* Builds the reference colour table (0x00RRGGBB). `table` must hold n ints and is updated IN PLACE with the
  * reference's write order, so stale entries survive exactly like m_Color does (kMono + invert quirk). */
 int jade_palette_build(int scheme, int n, int invert, int32_t* table);
+/* n in [1, 65536].  Transactional: every kernel keeps the table in shared memory, so a long table makes the engine fall back
+ * to kernels with a smaller footprint (default stereo N = 2048 configuration: the two-channel kernel up to 1384 colours, the
+ * per-channel ones up to ~27 000); if nothing fits the call fails with JADE_ERR_ARG and the PREVIOUS table, range and
+ * kernel choice stay in force.  The new table is uploaded in stream order: columns already pushed keep the old colours. */
 int jade_set_palette(jade_engine* e, const int32_t* rgb, int n);
 int jade_set_palette_scheme(jade_engine* e, int scheme, int n, int invert);
 int jade_set_value_range(jade_engine* e, float min_db, float max_db); /* swap / equal rules of the reference */
@@ -122,7 +126,11 @@ int jade_linear_crop(float fs, int bins, float fmin, float fmax, int* k_lo, int*
 int jade_log_rows(float fs, int fft_size, int rows, float fmin, float fmax, int32_t* lo, int32_t* hi);
 
 /* ---- streaming (real-time) path ---- */
-/* planar[ch] points to nsamples host floats; nch must equal config.channels.  Never blocks on the GPU. */
+/* planar[ch] points to nsamples host floats; nch must equal config.channels.  The audio-thread call: it copies the block
+ * into a pinned staging slot and launches two kernels; it never waits for GPU work (the only event it checks guards the
+ * reuse of a staging slot eight pushes later) and the engine lock it takes is never held by another call across a GPU
+ * synchronisation or a ring-sized copy -- jade_set_value_range / jade_set_palette / jade_set_window / jade_recolor_ring
+ * from the GUI thread delay it by microseconds.  Only jade_configure / jade_reset (the reference's buildmem()) stop it. */
 int jade_push_samples(jade_engine* e, const float* const* planar, int nch, int nsamples);
 /* Copies the columns produced since the previous fetch (oldest first, at most max_cols -- older ones are dropped
  * like the reference's ring overwrite) into pixels[ncols][rows] and, if not NULL, db[ncols][bins].  *first_col is
@@ -132,7 +140,9 @@ int jade_push_samples(jade_engine* e, const float* const* planar, int nch, int n
 int jade_fetch_columns(jade_engine* e, uint32_t* pixels, float* db, int max_cols, int* ncols, int64_t* first_col);
 int jade_ring_info(jade_engine* e, int* ring_columns, int* rows, int* bins, int64_t* total_columns);
 /* Re-colour the whole ring from the stored dB values with the current palette/range (m_recomputeAll path,
- * Spectrogram.cpp:623-657).  pixels[ring_columns][rows], ring order (slot = column % ring_columns). */
+ * Spectrogram.cpp:623-657).  pixels[ring_columns][rows], ring order (slot = column % ring_columns); every row map
+ * (log max-pool rows take the largest dB of their band).  Columns pushed WHILE the call copies the ring may be caught
+ * half-written in `pixels`; they are returned complete by the next jade_fetch_columns. */
 int jade_recolor_ring(jade_engine* e, uint32_t* pixels);
 /* dB ring exactly as stored (slot order), db[ring_columns][bins]; unwritten slots hold -120 (Spectrogram.cpp:223) */
 int jade_read_ring_db(jade_engine* e, float* db);
@@ -178,9 +188,11 @@ int jade_host_free(void* p);
 
 /* ---- introspection ---- */
 int64_t jade_kernel_launches(jade_engine* e); /* kernels launched by this engine so far */
-/* name of the kernel family the current configuration dispatches to ("warp<T>", "cta<R1>", "cta2<R1>") */
+/* name of the kernel the current configuration dispatches interior, aligned frames to ("pkz2048", "pk2048",
+ * "pksmall<T>", "pkcta<R1>", "pkcta2<16>", "warp<T>", "cta<R1>") */
 const char* jade_kernel_name(jade_engine* e);
-/* seconds of device time of the most recent jade_render_device / render_batch kernels (CUDA events) */
+/* seconds of device time of the kernels of the most recent jade_render_device call (CUDA events on its stream); -1 before
+ * the first one.  jade_render_batch overlaps copies and kernels on several streams and is not covered. */
 double jade_last_kernel_seconds(jade_engine* e);
 
 #ifdef __cplusplus

@@ -25,6 +25,7 @@
 #include "jade_pk.cuh"
 #include "jade_pk_cta.cuh"
 #include "jade_pk_small.cuh"
+#include "jade_pkz.cuh"
 
 using jade::KParams;
 
@@ -56,7 +57,8 @@ kernel_fn cta_kernel(int R1, int mixk, bool general);             // jade_k_cta.
 kernel_fn pkcta_kernel(int R1, int mixk, bool want_db);           // jade_k_pkcta.cu
 kernel_fn pkcta2_kernel(int mixk);                                // jade_k_pkcta.cu
 kernel_fn pk2048_kernel(int mixk, bool want_db, int load);        // jade_k_pk.cu (load = jade::PK_LD_*)
-kernel_fn pk2048x2_kernel(bool want_db);                           // jade_k_pk2.cu (stereo: both channels per warp)
+kernel_fn pk2048x2_kernel(bool want_db);                           // jade_k_pk2.cu (stereo: two real transforms per warp; experiments)
+kernel_fn pkz2048_kernel(bool want_db, bool guard);                // jade_k_pkz.cu (stereo: one complex transform per frame)
 kernel_fn pksmall_kernel(int T, int mixk, bool want_db, bool guard); // jade_k_pksmall_a.cu / _b.cu
 } // namespace jade_k
 namespace {
@@ -115,8 +117,19 @@ struct jade_engine {
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
     bool timed = false;
     std::string err;
-    std::mutex mu;
+    // Locking.  `mu` guards the plain engine state and is only ever held for short host-side
+    // sections and asynchronous launches: no call holds it across a cudaStreamSynchronize / cudaEventSynchronize on GPU work
+    // it has just submitted, a blocking cudaMemcpy or a ring-sized host copy, so the audio thread (jade_push_samples)
+    // never waits behind the GUI thread's GPU work.  `ctl_mu` serialises the control operations (configure, reset,
+    // set_window, set_palette, recolor) among themselves; lock order is ctl_mu, then mu.
+    std::mutex mu, ctl_mu;
     std::atomic<long long> launches{0};
+    int smem_optin = 227 * 1024; // largest dynamic shared-memory size a kernel may opt in to
+    // pinned staging for table uploads that must not synchronise (palette, window): two slots, in-stream copies
+    PinBuf h_tab[2];
+    cudaEvent_t tab_ev[2] = {nullptr, nullptr};
+    int tab_slot = 0;
+    cudaEvent_t ctl_ev = nullptr;
 
     bool configured = false;
     jade_config cfg{};
@@ -190,6 +203,25 @@ int upload(jade_engine* e, DevBuf& b, const void* src, size_t bytes)
     return 0;
 }
 
+// Table upload that never synchronises with the GPU work in flight: the bytes go through one of two pinned staging slots
+// and are copied in stream order on the engine's stream (kernels launched earlier still see the old table, later ones the
+// new one); the batch pipeline streams are made to wait for the copy.  `b` must already be large enough (no reallocation:
+// cudaFree would synchronise the device).  Caller holds e->mu.
+int upload_async(jade_engine* e, DevBuf& b, const void* src, size_t bytes)
+{
+    if (bytes > b.bytes) return fail(e, JADE_ERR_STATE, "internal: table buffer too small (%zu > %zu)", bytes, b.bytes);
+    if (!bytes) return 0;
+    const int slot = e->tab_slot;
+    e->tab_slot ^= 1;
+    if (e->h_tab[slot].ensure(std::max<size_t>(bytes, 256 * 1024))) return fail(e, JADE_ERR_CUDA, "pinned table staging allocation failed");
+    CU(e, cudaEventSynchronize(e->tab_ev[slot])); // the copy that used this slot two uploads ago: long complete
+    memcpy(e->h_tab[slot].p, src, bytes);
+    CU(e, cudaMemcpyAsync(b.p, e->h_tab[slot].p, bytes, cudaMemcpyHostToDevice, e->stream));
+    CU(e, cudaEventRecord(e->tab_ev[slot], e->stream));
+    for (int i = 0; i < kPipe; ++i) CU(e, cudaStreamWaitEvent(e->pipe_stream[i], e->tab_ev[slot], 0));
+    return 0;
+}
+
 int choose_kernel(jade_engine* e)
 {
     KernelChoice kc;
@@ -197,7 +229,19 @@ int choose_kernel(jade_engine* e)
     const int N = e->N;
     const int mu = e->mixk;
     const bool po = e->general;
-    if (N >= 128 && N <= 2048 && !po && mu != jade::MIX_SEL) {
+    // Every kernel keeps the palette in shared memory, so a long table can push an instantiation over the opt-in limit.
+    // Degrade instead of failing: two-channel complex kernel -> per-channel packed kernels -> general kernels; only when
+    // nothing fits does configuration / jade_set_palette fail (and jade_set_palette then restores the previous table).
+    auto pk_smem = [&](int T) {
+        switch (T) {
+        case 2: return jade::PkSmallCfg<2>::smem_bytes(e->npal);
+        case 4: return jade::PkSmallCfg<4>::smem_bytes(e->npal);
+        case 8: return jade::PkSmallCfg<8>::smem_bytes(e->npal);
+        case 16: return jade::PkSmallCfg<16>::smem_bytes(e->npal);
+        default: return jade::PkCfg::smem_bytes(e->npal);
+        }
+    };
+    if (N >= 128 && N <= 2048 && !po && mu != jade::MIX_SEL && pk_smem(N / 64) <= e->smem_optin) {
         // fast path: packed-FP32x2 kernels (jade_pk.cuh for N = 2048, jade_pk_small.cuh below)
         const int T = N / 64;
         kc.family = 3;
@@ -239,16 +283,33 @@ int choose_kernel(jade_engine* e)
             km.blocks_per_sm = occ_m;
             e->kc_mid = km;
             e->has_mid = true;
-            // stereo kernel: the two channels of a frame share every table read
+            // AbsMean over exactly two channels: both channels of a frame as ONE complex transform (jade_pkz.cuh).  Its
+            // rounding differs from the per-channel kernels, so EVERY column of such a configuration goes through it:
+            // interior aligned frames through the TMA-staged instantiation, everything else through its guarded one.
             const int contributing = (e->cfg.mix_mode == JADE_MIX_LEFT || e->cfg.mix_mode == JADE_MIX_RIGHT) ? 1 : e->cfg.channels;
-            if (mu == jade::MIX_SUM && contributing == 2) {
+            static const bool old_pair = [] { const char* v = getenv("JADE_PK_LOAD"); return v && !strcmp(v, "pair2"); }(); // experiments
+            const int pair_smem = old_pair ? jade::PkPairCfg::smem_bytes(e->npal) : jade::PkzCfg::smem_bytes(e->npal);
+            if (mu == jade::MIX_SUM && contributing == 2 && pair_smem <= e->smem_optin) {
                 KernelChoice kp = kc;
-                snprintf(kp.name, sizeof kp.name, "pk2048x2");
-                kp.threads = jade::PkPairCfg::WARPS * 32;
-                kp.units_per_block = jade::PkPairCfg::WARPS;
-                kp.smem = jade::PkPairCfg::smem_bytes(e->npal);
-                kp.fn = jade_k::pk2048x2_kernel(false);
-                kp.fn_db = jade_k::pk2048x2_kernel(true);
+                if (old_pair) {
+                    snprintf(kp.name, sizeof kp.name, "pk2048x2");
+                    kp.threads = jade::PkPairCfg::WARPS * 32;
+                    kp.units_per_block = jade::PkPairCfg::WARPS;
+                    kp.smem = jade::PkPairCfg::smem_bytes(e->npal);
+                    kp.fn = jade_k::pk2048x2_kernel(false);
+                    kp.fn_db = jade_k::pk2048x2_kernel(true);
+                } else {
+                    snprintf(kp.name, sizeof kp.name, "pkz2048");
+                    kp.threads = jade::PkzCfg::WARPS * 32;
+                    kp.units_per_block = jade::PkzCfg::WARPS;
+                    kp.smem = jade::PkzCfg::smem_bytes(e->npal);
+                    kp.fn = jade_k::pkz2048_kernel(false, false);
+                    kp.fn_db = jade_k::pkz2048_kernel(true, false);
+                    ke = kp;
+                    snprintf(ke.name, sizeof ke.name, "pkz2048-guard");
+                    ke.fn = jade_k::pkz2048_kernel(true, true);
+                    e->has_mid = false; // 8- but not 16-byte aligned frames: the guarded instantiation
+                }
                 CU(e, cudaFuncSetAttribute((const void*)kp.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.smem));
                 CU(e, cudaFuncSetAttribute((const void*)kp.fn_db, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.smem));
                 int occ_p = 0;
@@ -315,6 +376,9 @@ int choose_kernel(jade_engine* e)
     } else {
         return fail(e, JADE_ERR_ARG, "unsupported fft_size %d (power of two in [64,65536])", N);
     }
+    if (kc.smem > e->smem_optin)
+        return fail(e, JADE_ERR_ARG, "kernel %s needs %d bytes of shared memory with a %d-colour palette (limit %d)", kc.name, kc.smem,
+                    e->npal, e->smem_optin);
     CU(e, cudaFuncSetAttribute((const void*)kc.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kc.smem));
     int occ = 0;
     CU(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)kc.fn, kc.threads, kc.smem));
@@ -452,7 +516,8 @@ int launch_stft(jade_engine* e, KParams& P, cudaStream_t st)
     if (e->kc.family != 3) return launch_one(e, e->kc, P, st);
     // packed kernels: interior, aligned frames (16 bytes: cp.async staging for N = 2048; 8 bytes: LDG.64); the rest goes
     // to the guarded-load instantiation
-    if (!P.aligned2) return launch_one(e, e->kc_edge, P, st);
+    static const bool force_guard = [] { const char* v = getenv("JADE_PK_LOAD"); return v && !strcmp(v, "guard"); }(); // experiments
+    if (!P.aligned2 || force_guard) return launch_one(e, e->kc_edge, P, st);
     if (!e->has_mid && !P.aligned4) return launch_one(e, e->kc_edge, P, st); // N < 2048: the staged kernel or the guarded one
     static const bool force_ldg = [] { const char* v = getenv("JADE_PK_LOAD"); return v && !strcmp(v, "ldg"); }(); // experiments
     static const bool no_pair = [] { const char* v = getenv("JADE_PK_LOAD"); return v && !strcmp(v, "single"); }();
@@ -484,22 +549,32 @@ uint32_t bake_pixel(int32_t rgb, int fmt)
     return 0xFF000000u | (r << 16) | (g << 8) | b;                           // Spectrogram.cpp:637
 }
 
-int upload_palette(jade_engine* e)
+constexpr int kMaxPalette = 65536; // jade_set_palette's argument limit; the device table is allocated for it once
+
+// async = true: in stream order through pinned staging, no synchronisation (set_palette / set_window while streaming)
+int upload_palette(jade_engine* e, bool async = false)
 {
     std::vector<uint32_t> baked(e->h_palette.size());
     for (size_t i = 0; i < baked.size(); ++i) baked[i] = bake_pixel(e->h_palette[i], e->cfg.pixel_format);
     e->npal = (int)baked.size();
-    return upload(e, e->d_palette, baked.data(), baked.size() * 4);
+    if (e->d_palette.ensure((size_t)kMaxPalette * 4)) return fail(e, JADE_ERR_CUDA, "palette allocation failed");
+    return async ? upload_async(e, e->d_palette, baked.data(), baked.size() * 4) : upload(e, e->d_palette, baked.data(), baked.size() * 4);
 }
 
-int upload_window(jade_engine* e)
+// device copy of a unit-RMS window: x 0.5 (real-FFT split without the 1/2; the two-channel complex transform folds its
+// 1/4 the same way) x sqrt(power_scale)
+void device_window(const jade_engine* e, const std::vector<float>& unit, std::vector<float>& w)
 {
-    jade_host::make_window(e->cfg.window, e->N, e->h_window);
-    // device copy: x 0.5 (real-FFT split without the 1/2) x sqrt(power_scale)
-    std::vector<float> w(e->h_window);
+    w = unit;
     const float ps = e->cfg.power_scale;
     const float g = (ps == 1.0f) ? 0.5f : 0.5f * std::sqrt(ps);
     for (auto& v : w) v *= g;
+}
+int upload_window(jade_engine* e)
+{
+    jade_host::make_window(e->cfg.window, e->N, e->h_window);
+    std::vector<float> w;
+    device_window(e, e->h_window, w);
     return upload(e, e->d_window, w.data(), w.size() * 4);
 }
 
@@ -560,6 +635,7 @@ int jade_create(int device, jade_engine** out)
     cudaDeviceProp prop;
     CU(e, cudaGetDeviceProperties(&prop, device));
     e->sm_count = prop.multiProcessorCount;
+    e->smem_optin = (int)prop.sharedMemPerBlockOptin;
     CU(e, cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     for (int i = 0; i < kPipe; ++i) {
         CU(e, cudaStreamCreateWithFlags(&e->pipe_stream[i], cudaStreamNonBlocking));
@@ -569,6 +645,8 @@ int jade_create(int device, jade_engine** out)
     CU(e, cudaEventCreate(&e->ev_t1));
     for (int i = 0; i < kStageSlots; ++i) CU(e, cudaEventCreateWithFlags(&e->stage_ev[i], cudaEventDisableTiming));
     CU(e, cudaEventCreateWithFlags(&e->last_push_ev, cudaEventDisableTiming));
+    CU(e, cudaEventCreateWithFlags(&e->ctl_ev, cudaEventDisableTiming));
+    for (int i = 0; i < 2; ++i) CU(e, cudaEventCreateWithFlags(&e->tab_ev[i], cudaEventDisableTiming));
     // default palette: the component's (256 colours, kJade, -50..50 dB; Spectrogram.cpp:337,342)
     e->h_palette.assign(256, 0);
     jade_host::palette_build(JADE_PAL_JADE, 256, 0, e->h_palette.data());
@@ -600,6 +678,11 @@ int jade_destroy(jade_engine* e)
     for (int i = 0; i < kStageSlots; ++i)
         if (e->stage_ev[i]) cudaEventDestroy(e->stage_ev[i]);
     if (e->last_push_ev) cudaEventDestroy(e->last_push_ev);
+    if (e->ctl_ev) cudaEventDestroy(e->ctl_ev);
+    for (int i = 0; i < 2; ++i) {
+        if (e->tab_ev[i]) cudaEventDestroy(e->tab_ev[i]);
+        e->h_tab[i].release();
+    }
     if (e->ev_t0) cudaEventDestroy(e->ev_t0);
     if (e->ev_t1) cudaEventDestroy(e->ev_t1);
     if (e->stream) cudaStreamDestroy(e->stream);
@@ -647,6 +730,9 @@ int jade_config_set_feed_percent(jade_config* c, int percent)
 int jade_configure(jade_engine* e, const jade_config* cin)
 {
     if (!e || !cin) return fail(e, JADE_ERR_ARG, "null argument");
+    // buildmem(): a stop-the-world reconfiguration like the reference's (setFFTSize holds m_protect, Spectrogram.cpp:162-167);
+    // a concurrent jade_push_samples waits for it
+    std::lock_guard<std::mutex> ctl(e->ctl_mu);
     std::lock_guard<std::mutex> lk(e->mu);
     CU(e, cudaSetDevice(e->device));
     jade_config c = *cin;
@@ -662,8 +748,11 @@ int jade_configure(jade_engine* e, const jade_config* cin)
     if (c.power_scale <= 0.f) c.power_scale = 1.f;
     if (c.sample_rate <= 0.f) return fail(e, JADE_ERR_ARG, "sample_rate must be positive");
     if (c.max_push <= 0) c.max_push = c.fft_size;
-    if ((long long)(c.frames_per_block - 1) * c.hop > c.block_stride + c.fft_size)
-        return fail(e, JADE_ERR_ARG, "frames_per_block*hop exceeds the block");
+    // frame starts must be monotone in the column index (columns_available, the interior / boundary split of launch_stft and
+    // the chunking of jade_render_batch rely on it): the last sub-frame of a block may not start after the next block
+    if ((long long)(c.frames_per_block - 1) * c.hop > c.block_stride)
+        return fail(e, JADE_ERR_ARG, "(frames_per_block-1)*hop = %lld exceeds block_stride %d: frame starts would not be monotone",
+                    (long long)(c.frames_per_block - 1) * c.hop, c.block_stride);
 
     e->configured = false;
     e->cfg = c;
@@ -775,11 +864,15 @@ int jade_set_window(jade_engine* e, int window)
 {
     if (!e || window < 0 || window > JADE_WIN_HANNPOISSON) return fail(e, JADE_ERR_ARG, "bad window");
     if (!e->configured) return fail(e, JADE_ERR_STATE, "engine not configured");
-    std::lock_guard<std::mutex> lk(e->mu);
+    std::lock_guard<std::mutex> ctl(e->ctl_mu);
     CU(e, cudaSetDevice(e->device));
-    CU(e, cudaStreamSynchronize(e->stream));
+    std::vector<float> unit, w;
+    jade_host::make_window(window, e->N, unit); // outside e->mu: up to N double cos calls
+    device_window(e, unit, w);
+    std::lock_guard<std::mutex> lk(e->mu);
     e->cfg.window = window;
-    return upload_window(e);
+    e->h_window.swap(unit);
+    return upload_async(e, e->d_window, w.data(), w.size() * 4); // pushes already launched keep the old table
 }
 
 int jade_get_window(jade_engine* e, float* out, int n)
@@ -804,7 +897,8 @@ int jade_reset(jade_engine* e)
 {
     if (!e) return JADE_ERR_ARG;
     if (!e->configured) return fail(e, JADE_ERR_STATE, "engine not configured");
-    std::lock_guard<std::mutex> lk(e->mu);
+    std::lock_guard<std::mutex> ctl(e->ctl_mu);
+    std::lock_guard<std::mutex> lk(e->mu); // buildmem(): stop-the-world, see jade_configure
     CU(e, cudaSetDevice(e->device));
     CU(e, cudaStreamSynchronize(e->stream));
     return reset_stream_state(e);
@@ -820,20 +914,41 @@ int jade_palette_build(int scheme, int n, int invert, int32_t* table)
 
 int jade_set_palette(jade_engine* e, const int32_t* rgb, int n)
 {
-    if (!e || !rgb || n < 1 || n > 65536) return fail(e, JADE_ERR_ARG, "bad palette");
+    if (!e || !rgb || n < 1 || n > kMaxPalette) return fail(e, JADE_ERR_ARG, "bad palette (1..%d colours)", kMaxPalette);
+    std::lock_guard<std::mutex> ctl(e->ctl_mu);
     std::lock_guard<std::mutex> lk(e->mu);
     CU(e, cudaSetDevice(e->device));
     const bool resize = (int)e->h_palette.size() != n;
+    // transaction: everything the new table changes is saved and put back if no kernel fits it
+    std::vector<int32_t> old_pal(e->h_palette);
+    const int old_npal = e->npal;
+    const float old_mult = e->range.mult;
+    struct Choice {
+        KernelChoice kc, kc_edge, kc_mid, kc_pair;
+        bool has_mid, has_pair;
+    } old_choice{e->kc, e->kc_edge, e->kc_mid, e->kc_pair, e->has_mid, e->has_pair};
     e->h_palette.assign(rgb, rgb + n);
     e->range.mult = float(n) / (e->range.mx - e->range.mn); // CColorpalette.cpp:55-61 setNrOfColors
-    if (e->configured) {
-        CU(e, cudaStreamSynchronize(e->stream));
-        for (int i = 0; i < kPipe; ++i) CU(e, cudaStreamSynchronize(e->pipe_stream[i]));
-        if (int r = upload_palette(e)) return r;
-        if (resize)
-            if (int r = choose_kernel(e)) return r; // shared-memory size depends on the table length
-    } else {
+    if (!e->configured) {
         e->npal = n;
+        return JADE_OK;
+    }
+    e->npal = n;
+    int r = resize ? choose_kernel(e) : 0; // shared-memory size depends on the table length
+    if (!r) r = upload_palette(e, true);  // in stream order: no wait for the kernels in flight
+    if (r) {
+        const std::string why = e->err;
+        e->h_palette.swap(old_pal);
+        e->npal = old_npal;
+        e->range.mult = old_mult;
+        e->kc = old_choice.kc;
+        e->kc_edge = old_choice.kc_edge;
+        e->kc_mid = old_choice.kc_mid;
+        e->kc_pair = old_choice.kc_pair;
+        e->has_mid = old_choice.has_mid;
+        e->has_pair = old_choice.has_pair;
+        upload_palette(e, true);
+        return fail(e, r, "%s; previous palette kept", why.c_str());
     }
     return JADE_OK;
 }
@@ -912,7 +1027,8 @@ int jade_push_samples(jade_engine* e, const float* const* planar, int nch, int n
     if (e->hist_fill + nsamples > e->hist_cap) {
         const long long next_start = frame_start_abs(c, e->frames_done); // oldest sample still needed
         long long from = next_start - e->hist_base_abs;
-        if (from < 0) from = 0;
+        // hop > fft_size: the next frame may start beyond everything pushed so far -- nothing older is needed then
+        from = std::min<long long>(std::max<long long>(from, 0), e->hist_fill);
         from &= ~3LL; // keep frame starts 16-byte aligned relative to the buffer (TMA-staged kernels)
         keep = (int)(e->hist_fill - from);
         slide_from = from;
@@ -965,9 +1081,11 @@ int jade_push_samples(jade_engine* e, const float* const* planar, int nch, int n
             P.ring_col0 = e->emitted + skip;
             // Arm the columns for polling: every pixel carries alpha 0xFF (bake_pixel), so a zeroed slot that has become
             // non-zero everywhere has been written completely -- jade_fetch_columns can hand it out without waiting for
-            // the kernel to retire and its event to signal.  Only for a handful of columns of a long ring (the slots
-            // cannot still be the target of an earlier launch); otherwise fetch falls back to the event.
-            if (n <= 8 && e->W >= 64) {
+            // the kernel to retire and its event to signal.  Only for a handful of columns of a long ring: up to kStageSlots
+            // earlier pushes of <= 8 columns each can still be in flight, so with W >= (kStageSlots + 1) * 8 the slots
+            // zeroed here cannot be the target of a launch that is still running; otherwise fetch falls back to the event.
+            // INVARIANT: every pixel format bakes a non-zero alpha byte (bake_pixel), so no complete pixel is ever 0.
+            if (n <= 8 && e->W >= (kStageSlots + 1) * 8) {
                 uint32_t* ring = (uint32_t*)e->h_pixring.p;
                 for (long long i = 0; i < n; ++i) memset(ring + (size_t)((P.ring_col0 + i) % e->W) * e->R, 0, (size_t)e->R * 4);
             } else {
@@ -1056,19 +1174,26 @@ int jade_recolor_ring(jade_engine* e, uint32_t* pixels)
 {
     if (!e || !pixels) return fail(e, JADE_ERR_ARG, "null argument");
     if (!e->configured) return fail(e, JADE_ERR_STATE, "engine not configured");
-    if (e->pooled) return fail(e, JADE_ERR_ARG, "recolor needs a per-bin row map (identity / linear crop)");
-    std::lock_guard<std::mutex> lk(e->mu);
+    std::lock_guard<std::mutex> ctl(e->ctl_mu);
     CU(e, cudaSetDevice(e->device));
-    KParams P;
-    fill_params(e, P);
-    P.pix = (uint32_t*)e->h_pixring.p;
-    const float* dbc = (const float*)e->d_dbring.p;
-    long long ncolumns = e->W;
-    void* args[] = {&P, &dbc, &ncolumns};
-    const int grid = (int)std::min<long long>(ncolumns, (long long)e->sm_count * 8);
-    CU(e, cudaLaunchKernel((const void*)jade::recolor_kernel, dim3(grid), dim3(256), args, 0, e->stream));
-    e->launches++;
-    CU(e, cudaStreamSynchronize(e->stream));
+    {
+        // only the launch happens under e->mu: a concurrent jade_push_samples waits microseconds, not for the kernel
+        std::lock_guard<std::mutex> lk(e->mu);
+        KParams P;
+        fill_params(e, P);
+        P.pix = (uint32_t*)e->h_pixring.p;
+        const float* dbc = (const float*)e->d_dbring.p;
+        long long ncolumns = e->W;
+        void* args[] = {&P, &dbc, &ncolumns};
+        const int grid = (int)std::min<long long>(ncolumns, (long long)e->sm_count * 8);
+        CU(e, cudaLaunchKernel((const void*)jade::recolor_kernel, dim3(grid), dim3(256), args, 0, e->stream));
+        e->launches++;
+        CU(e, cudaEventRecord(e->ctl_ev, e->stream));
+        e->poll_from = e->emitted; // slots the kernel rewrites cannot be polled for "non-zero = complete" any more
+    }
+    CU(e, cudaEventSynchronize(e->ctl_ev));
+    // Columns pushed while this copy runs are written by later kernels and may be caught half-way; they are complete in
+    // the next jade_fetch_columns, which returns every column emitted since the previous fetch.
     memcpy(pixels, e->h_pixring.p, (size_t)e->W * e->R * 4);
     return JADE_OK;
 }

@@ -1,0 +1,13 @@
+// jade_k_pkz.cu -- instantiations of the N = 2048 stereo kernel that transforms both channels as one complex signal
+// (jade_pkz.cuh); dispatch in jade_gpu.cu.
+#include "jade_pkz.cuh"
+namespace jade_k {
+typedef void (*kernel_fn)(const jade::KParams);
+// guard: bounds-checked global loads (boundary columns, unaligned geometries); otherwise TMA-staged interior frames
+kernel_fn pkz2048_kernel(bool want_db, bool guard)
+{
+    using namespace jade;
+    if (guard) return want_db ? (kernel_fn)stft_pkz2048_kernel<true, PKZ_GUARD> : (kernel_fn)stft_pkz2048_kernel<false, PKZ_GUARD>;
+    return want_db ? (kernel_fn)stft_pkz2048_kernel<true, PKZ_ASYNC> : (kernel_fn)stft_pkz2048_kernel<false, PKZ_ASYNC>;
+}
+} // namespace jade_k

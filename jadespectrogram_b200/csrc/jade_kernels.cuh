@@ -643,6 +643,15 @@ JADE_KERNEL(256) recolor_kernel(const KParams P, const float* dbcols, long long 
     for (long long c = blockIdx.x; c < ncolumns; c += gridDim.x) {
         const float* d = dbcols + c * P.B;
         uint32_t* o = P.pix + c * P.R;
+        if (P.pooled) { // log max-pool rows: 10 log10 is monotone, so the band's largest dB value is the dB of its largest power
+            for (int r = threadIdx.x; r < P.R; r += blockDim.x) {
+                const i2 rb = P.row_bins[r];
+                float mx = d[rb.lo];
+                for (int k = rb.lo + 1; k < rb.hi; ++k) mx = fmaxf(mx, d[k]);
+                o[P.flip ? (P.R - 1 - r) : r] = colour_of(mx, P, P.palette);
+            }
+            continue;
+        }
         for (int k = P.k_lo + threadIdx.x; k < P.k_hi; k += blockDim.x) {
             const int row = P.flip ? (P.k_hi - 1 - k) : (k - P.k_lo);
             o[row] = colour_of(d[k], P, P.palette);

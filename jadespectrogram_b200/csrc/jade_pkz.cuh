@@ -1,0 +1,355 @@
+// jade_pkz.cuh -- N = 2048, AbsMean over exactly two channels (BASELINE configs[1], the plugin's live default): both channels
+// of a frame in ONE 2048-point complex transform.
+//
+// The reference computes each channel's power spectrum and averages them (Spectrogram.cpp:52-58,67-74).  With
+//     z[n] = w[n] (x_L[n] + i x_R[n]),   Z = DFT_2048(z):     X_L[k] = (Z[k] + conj Z[N-k]) / 2,   X_R[k] = (Z[k] - conj Z[N-k]) / 2i
+//     |X_L[k]|^2 + |X_R[k]|^2 = ( |Z[k]|^2 + |Z[N-k]|^2 ) / 2
+// so the two real transforms, their pair splits (96 packed instructions and 32 64-bit shuffles per channel in
+// stft_pk2048x2_kernel, jade_pk.cuh) and the split-twiddle table disappear for one extra radix-2 stage, and only |Z|^2
+// is ever needed.  The device window table carries the factor 1/2 (upload_window), hence mean power = |Z'[k]|^2 + |Z'[N-k]|^2.
+//
+// One warp transforms one stereo frame: n = s + 32 n1 (lane s, n1 = 0..63), 64-point DFT over n1 in registers (window
+// fused into its first stage), one transpose through shared memory, twisted 32-point DFTs over s (inter-pass twiddle
+// W_2048^{s k1} folded into the butterflies, fft32_twisted).  Lane l takes the two rows k1 = l and k1 = 64 - l (lane 0:
+// rows 0 and 32): bin k = k1 + 64 k2 and its mirror N - k = (64 - k1) + 64 (31 - k2) then sit in the SAME lane, so the
+// mirror sum needs no shuffle at all -- nothing crosses lanes after the transpose.  Lane l emits the bins l + 64 k2 and
+// (64 - l) + 64 k2, k2 = 0..15: per k2 the warp stores two runs of 32 consecutive rows.
+//
+// Epilogue per bin: log2 (MUFU), one FFMA to the palette position, F2I, ONE integer clamp to [0, npal] (entry npal of the
+// shared-memory table is the colour of the `value >= m_Max` rule), palette load, store; the + 1e-11 rides on the power FMAs.
+// (Tried and dropped, profiles/r02_pkz_variants.txt: interleaving this epilogue with the next frame's loads in one basic
+// block, -4 %; passing an "FP token" round-robin between the three warps of a scheduler through named barriers so that
+// only one of them runs a butterfly pass at a time, -6 %.)
+//
+// Interior, 16-byte aligned frames are staged by the TMA engine (cp.async.bulk, two 8 KB copies on one mbarrier) into
+// the warp's buffer -- the buffer the transpose went through a moment before; PKZ_GUARD instantiations read global
+// memory with bounds checks (boundary columns, unaligned geometries) and run the same arithmetic, so streaming, batch
+// and sharded renderings agree bit for bit.
+#pragma once
+#include "jade_pk.cuh"
+
+namespace jade {
+
+// cos(2 pi m / 64), m = 0..16
+JADE_HD constexpr float cos64_q(int m)
+{
+    return m == 0 ? 1.0f
+         : m == 1 ? 0.99518472667219692873f
+         : m == 2 ? 0.98078528040323043058f
+         : m == 3 ? 0.95694033573220882438f
+         : m == 4 ? 0.92387953251128673848f
+         : m == 5 ? 0.88192126434835504956f
+         : m == 6 ? 0.83146961230254523567f
+         : m == 7 ? 0.77301045336273699338f
+         : m == 8 ? 0.70710678118654757274f
+         : m == 9 ? 0.63439328416364548779f
+         : m == 10 ? 0.55557023301960228867f
+         : m == 11 ? 0.47139673682599780857f
+         : m == 12 ? 0.38268343236508983729f
+         : m == 13 ? 0.29028467725446233105f
+         : m == 14 ? 0.19509032201612833135f
+         : m == 15 ? 0.09801714032956077016f
+                   : 0.0f;
+}
+JADE_HD constexpr float cos64(int m) { return m <= 16 ? cos64_q(m) : -cos64_q(32 - m); }
+JADE_HD constexpr float sin64(int m) { return m <= 16 ? cos64_q(16 - m) : cos64_q(m - 16); }
+JADE_HD constexpr int brev6(int v) { return (brev5(v & 31) << 1) | (v >> 5); }
+
+// radix-2 DIT butterfly with W = exp(-2 pi i M64/64), M64 in [0, 32)
+template <int M64>
+JADE_DEVICE void bfly2_64(f2& a, f2& b)
+{
+    if (M64 == 0) {
+        const f2 t = b;
+        b = sub2(a, t);
+        a = add2(a, t);
+    } else if (M64 == 16) {
+        const f2 t = mul_mi(b);
+        b = sub2(a, t);
+        a = add2(a, t);
+    } else {
+        constexpr float c = cos64(M64);
+        constexpr float s = sin64(M64);
+        const f2 n = fma2(mul_mi(b), pk(s, s), fma2(b, pk(c, c), a));
+        b = fma2(a, pk(2.0f, 2.0f), neg2(n));
+        a = n;
+    }
+}
+template <int LEN, int BASE, int J>
+JADE_DEVICE void pk64_inner(f2* a)
+{
+    if constexpr (J < LEN / 2) {
+        bfly2_64<(J * 64) / LEN>(a[BASE + J], a[BASE + J + LEN / 2]);
+        pk64_inner<LEN, BASE, J + 1>(a);
+    }
+}
+template <int LEN, int BASE>
+JADE_DEVICE void pk64_blocks(f2* a)
+{
+    if constexpr (BASE < 64) {
+        pk64_inner<LEN, BASE, 0>(a);
+        pk64_blocks<LEN, BASE + LEN>(a);
+    }
+}
+// stages 2..6 of the in-place 64-point DFT (bit-reversed input, natural-order output); stage 1 is win_stage1_64
+JADE_DEVICE void fft64_pk_after_stage1(f2* a)
+{
+    pk64_blocks<4, 0>(a);
+    pk64_blocks<8, 0>(a);
+    pk64_blocks<16, 0>(a);
+    pk64_blocks<32, 0>(a);
+    pk64_blocks<64, 0>(a);
+}
+// window multiply fused with stage 1: pairs n1 = j and j + 32 (see win_stage1); the window is real here, so it is a
+// broadcast scalar operand
+JADE_DEVICE void win_stage1_64(f2* v, int j, f2 xa, float wa, f2 xb, float wb)
+{
+    const int i = brev5(j);
+    const f2 va = mul2(xa, pk(wa, wa));
+    v[2 * i] = fma2(xb, pk(wb, wb), va);
+    v[2 * i + 1] = fma2(neg2(xb), pk(wb, wb), va);
+}
+
+// exponent e of twisted-table entry t (0..15) of row k1 (0..63): the entry is W_2048^e  (cf. tw2_exponent)
+JADE_HD int twz_exponent(int k1, int t)
+{
+    if (t == 0) return 16 * k1;
+    if (t == 1) return 8 * k1;
+    if (t < 4) return 4 * (k1 + 64 * (t - 2));
+    if (t < 8) return 2 * (k1 + 64 * (t - 4));
+    return k1 + 64 * (t - 8);
+}
+// second row of lane l
+JADE_HD int pkz_row_b(int l) { return l == 0 ? 32 : 64 - l; }
+
+struct PkzCfg {
+    static constexpr int N = 2048, B = 1025;
+#ifndef JADE_PKZ_WARPS
+#define JADE_PKZ_WARPS 12
+#endif
+    static constexpr int WARPS = JADE_PKZ_WARPS;
+    static constexpr int WROW = 68;   // floats per lane row of the window table (64 + 16 B pad): conflict-free LDS.128
+    static constexpr int TROW = 18;   // f2 words per lane row of a twisted table (16 + 16 B pad)
+    static constexpr int XROW = 34;   // f2 words per transpose row
+    static constexpr int XCH = 64 * XROW; // f2 words per warp buffer (17 408 B): transpose, and landing area of the next frame
+    static constexpr int CH1 = 32 * XROW; // f2 offset of channel 1's 8 KB inside the buffer
+    static constexpr int off_win = 0;
+    static constexpr int off_twa = off_win + 32 * WROW * 4;
+    static constexpr int off_twb = off_twa + 32 * TROW * 8;
+    static constexpr int off_pal = off_twb + 32 * TROW * 8;
+    static JADE_HD int off_bar(int npal) { return off_pal + ((npal + 1) * 4 + 15) / 16 * 16; } // table + the `>= m_Max` entry
+    static JADE_HD int off_xch(int npal) { return off_bar(npal) + (WARPS * 8 + 15) / 16 * 16; }
+    static JADE_HD int smem_bytes(int npal) { return off_xch(npal) + WARPS * XCH * 8; }
+};
+
+enum { PKZ_ASYNC = 0, PKZ_GUARD = 1 };
+
+// Epilogue of one bin (cf. emit_bin): p already carries the reference's + 1e-11 (Spectrogram.cpp:36,107).  lg = log2 p; dB value
+// (optional) = 3.0103 lg; palette index = trunc(lg ck1 + ck0) clamped to [0, npal] by ONE integer min/max, where entry
+// npal of the shared-memory table holds the colour of CColorPalette's `value >= m_Max` rule (index of 0.9999 m_Max,
+// CColorpalette.h:34-35): lg ck1 + ck0 >= npal exactly when the dB value reaches m_Max.
+template <bool WANT_DB>
+JADE_DEVICE void pkz_emit(float p, uint32_t* pix, float* db, const KParams& P, const uint32_t* pal)
+{
+    const float lg = JADE_LOG2F(p);
+    const uint32_t c = pal[max(min((int)fm(lg, P.ck1, P.ck0), P.npal), 0)];
+    if (WANT_DB) {
+        if (db) *db = JADE_FMUL(3.01029995663981195f, lg);
+        if (pix) *pix = c;
+    } else {
+        *pix = c;
+    }
+}
+
+// (stream, column) walked incrementally: g -> g + gstep without a division per frame
+struct PkzWalk {
+    unsigned stream, col, dq, dr, ncols;
+    JADE_DEVICE void init(unsigned g, unsigned gstep, unsigned nc)
+    {
+        ncols = nc;
+        stream = g / nc;
+        col = g - stream * nc;
+        dq = gstep / nc;
+        dr = gstep - dq * nc;
+    }
+    JADE_DEVICE void next()
+    {
+        stream += dq;
+        col += dr;
+        if (col >= ncols) {
+            col -= ncols;
+            ++stream;
+        }
+    }
+};
+
+template <bool WANT_DB, int LD>
+JADE_KERNEL(PkzCfg::WARPS * 32, 1) stft_pkz2048_kernel(const KParams P)
+{
+    using Cfg = PkzCfg;
+    constexpr int WARPS = Cfg::WARPS;
+    JADE_DYN_SMEM(smem);
+    char* sm = reinterpret_cast<char*>(smem);
+    float* s_win = reinterpret_cast<float*>(sm + Cfg::off_win);
+    f2* s_twa = reinterpret_cast<f2*>(sm + Cfg::off_twa);
+    f2* s_twb = reinterpret_cast<f2*>(sm + Cfg::off_twb);
+    uint32_t* s_pal = reinterpret_cast<uint32_t*>(sm + Cfg::off_pal);
+    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(sm + Cfg::off_bar(P.npal));
+    f2* s_xch = reinterpret_cast<f2*>(sm + Cfg::off_xch(P.npal));
+
+    // ---- per-lane tables
+    for (int i = threadIdx.x; i < Cfg::N; i += blockDim.x) s_win[(i & 31) * Cfg::WROW + (i >> 5)] = P.window[i]; // n = s + 32 n1
+    if (LD == PKZ_ASYNC && threadIdx.x < WARPS) mbar_init(s_bar + threadIdx.x, 1);
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) {
+        const int l = i & 31, t = i >> 5;
+        const cpx a = P.twP[twz_exponent(l, t)]; // W_2048^e, e < 1024
+        s_twa[l * Cfg::TROW + t] = pk(a.x, a.y);
+        const cpx b = P.twP[twz_exponent(pkz_row_b(l), t)];
+        s_twb[l * Cfg::TROW + t] = pk(b.x, b.y);
+    }
+    for (int i = threadIdx.x; i <= P.npal; i += blockDim.x) s_pal[i] = P.palette[i < P.npal ? i : P.ci_hi];
+    __syncthreads();
+    grid_dep_wait();
+
+    const int s = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    f2* xw = s_xch + warp * Cfg::XCH;
+    const float* x0 = reinterpret_cast<const float*>(xw) + s;            // staged channel 0, sample s + 32 n1 at [32 n1]
+    const float* x1 = reinterpret_cast<const float*>(xw + Cfg::CH1) + s; //        channel 1
+    unsigned long long* bar = s_bar + warp;
+    unsigned copies = 0;
+    const float4* wrow = reinterpret_cast<const float4*>(s_win + s * Cfg::WROW);
+    const f2x2* trowa = reinterpret_cast<const f2x2*>(s_twa + s * Cfg::TROW);
+    const f2x2* trowb = reinterpret_cast<const f2x2*>(s_twb + s * Cfg::TROW);
+    const int kb = pkz_row_b(s);
+    const f2x2* rd_a = reinterpret_cast<const f2x2*>(xw + s * Cfg::XROW);
+    const f2x2* rd_b = reinterpret_cast<const f2x2*>(xw + kb * Cfg::XROW);
+
+    const unsigned total = (unsigned)P.ncols * (unsigned)P.nstreams;
+    const unsigned gstep = gridDim.x * WARPS;
+    const unsigned g0 = blockIdx.x * WARPS; // the CTA's first frame
+    if (g0 >= total) return;                // (CTA-uniform)
+    unsigned g = g0 + warp;
+    const unsigned my_iters = g < total ? (total - g + gstep - 1) / gstep : 0; // frames of this warp
+    PkzWalk cur, nxt;
+    cur.init(g < total ? g : 0u, gstep, (unsigned)P.ncols);
+    nxt = cur;
+
+    auto frame_ptr = [&](const PkzWalk& u, long long& st) { // channel 0 of the frame; st = its first sample index (may be < 0)
+        st = frame_start(P, P.first_col + u.col);
+        return P.samples + (long long)u.stream * P.stream_stride;
+    };
+    auto stage = [&](const PkzWalk& u) { // both channels of a frame -> the warp buffer (lane 0, after a __syncwarp())
+        long long st;
+        const float* a = frame_ptr(u, st) + st;
+        if (s == 0) bulk_copy2_g2s(xw, a, xw + Cfg::CH1, a + P.channel_stride, Cfg::N * 4, bar);
+#if defined(JADE_EMU)
+        __syncwarp();
+#endif
+    };
+    // samples x window and the first butterfly stage of the 64-point DFT over n1 -> v (bit-reversed order); pair j = n1 j, j + 32.
+    // c0 / st: channel-0 base and first sample index of the frame (PKZ_GUARD only).
+    auto load_pair = [&](f2* v, int j, const float* c0, long long st) {
+        const float4 wa4 = wrow[j / 4], wb4 = wrow[(j + 32) / 4];
+        const float wa = (j & 3) == 0 ? wa4.x : (j & 3) == 1 ? wa4.y : (j & 3) == 2 ? wa4.z : wa4.w;
+        const float wb = (j & 3) == 0 ? wb4.x : (j & 3) == 1 ? wb4.y : (j & 3) == 2 ? wb4.z : wb4.w;
+        if (LD == PKZ_ASYNC) {
+            win_stage1_64(v, j, pk(x0[32 * j], x1[32 * j]), wa, pk(x0[32 * (j + 32)], x1[32 * (j + 32)]), wb);
+        } else {
+            const float* c1 = c0 + P.channel_stride;
+            const long long ia = st + s + 32 * j, ib = ia + 1024;
+            const bool ina = ia >= 0 && ia < P.nsamples, inb = ib >= 0 && ib < P.nsamples;
+            win_stage1_64(v, j, pk(ina ? c0[ia] : 0.f, ina ? c1[ia] : 0.f), wa, pk(inb ? c0[ib] : 0.f, inb ? c1[ib] : 0.f), wb);
+        }
+    };
+
+    f2 v[64];
+    if (my_iters > 0) {
+        if (LD == PKZ_ASYNC) {
+            stage(cur);
+            mbar_wait(bar, copies & 1u);
+            ++copies;
+        }
+        long long st;
+        const float* c0 = frame_ptr(cur, st);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) load_pair(v, j, c0, st);
+        if (LD == PKZ_ASYNC) __syncwarp(); // every lane has read its samples before the transpose overwrites them
+    }
+
+    // eps = 1e-11 (Spectrogram.cpp:36) rides on the power FMAs: every output is the sum of one "low" power (register 0..15 of
+    // a row, seeded with eps) and one "high" power (16..31, unseeded); lane 0 pairs row 0 with itself, so its DC and Nyquist
+    // terms (register 0 / 16, added to themselves) carry eps / 2 each.
+    const float eps = 1e-11f, eps0 = s == 0 ? 0.5e-11f : 1e-11f, eps16 = s == 0 ? 0.5e-11f : 0.0f;
+
+    for (unsigned it = 0; it < my_iters;) {
+        const ColOut o = col_out(P, (int)cur.stream, P.first_col + cur.col);
+        fft64_pk_after_stage1(v); // v[k1] = Y[s, k1]
+#pragma unroll
+        for (int k1 = 0; k1 < 64; ++k1) xw[k1 * Cfg::XROW + s] = v[k1];
+        __syncwarp();
+        f2 ua[32], ub[32];
+#pragma unroll
+        for (int jx = 0; jx < 32; jx += 2) {
+            const f2x2 ta = rd_a[jx / 2], tb = rd_b[jx / 2];
+            ua[brev(jx, 5)] = ta.a;
+            ua[brev(jx + 1, 5)] = ta.b;
+            ub[brev(jx, 5)] = tb.a;
+            ub[brev(jx + 1, 5)] = tb.b;
+        }
+        __syncwarp(); // the buffer is free again
+        const bool more = it + 1 < my_iters;
+        if (more) {
+            nxt.next();
+            if (LD == PKZ_ASYNC) stage(nxt);
+        }
+        fft32_twisted(ua, trowa); // ua[k2] = Z[s  + 64 k2]
+        fft32_twisted(ub, trowb); // ub[k2] = Z[kb + 64 k2]
+        // mean power of bin k (+ eps): |Z[k]|^2 + |Z[N-k]|^2.  Row s: bins s + 64 k2 mirror into row 64 - s at 31 - k2 (lane 0: row 0
+        // at 32 - k2); row kb likewise into row s (lane 0: row 32 into itself).
+        float pa[32], pb[32];
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+            const float ea = q == 0 ? eps0 : q < 16 ? eps : q == 16 ? eps16 : 0.0f, eb = q < 16 ? eps : 0.0f;
+            pa[q] = fm(lo(ua[q]), lo(ua[q]), q <= 16 ? fm(hi(ua[q]), hi(ua[q]), ea) : JADE_FMUL(hi(ua[q]), hi(ua[q])));
+            pb[q] = fm(lo(ub[q]), lo(ub[q]), q < 16 ? fm(hi(ub[q]), hi(ub[q]), eb) : JADE_FMUL(hi(ub[q]), hi(ub[q])));
+        }
+        float oa[16], ob[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            oa[q] = JADE_FADD(pa[q], s == 0 ? pa[(32 - q) & 31] : pb[31 - q]);
+            ob[q] = JADE_FADD(pb[q], s == 0 ? pb[31 - q] : pa[31 - q]);
+        }
+        const float omid = JADE_FADD(pa[16], pa[16]); // bin 1024 (lane 0)
+
+        // ---- epilogue: dB, palette, store
+        {
+            uint32_t* p_a = o.pix ? o.pix + (1024 - s) : nullptr;  // bin k -> row 1024 - k
+            uint32_t* p_b = o.pix ? o.pix + (1024 - kb) : nullptr;
+            float* d_a = (WANT_DB && o.db) ? o.db + s : nullptr;
+            float* d_b = (WANT_DB && o.db) ? o.db + kb : nullptr;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                pkz_emit<WANT_DB>(oa[q], (!WANT_DB || p_a) ? p_a - 64 * q : nullptr, d_a ? d_a + 64 * q : nullptr, P, s_pal);
+                pkz_emit<WANT_DB>(ob[q], (!WANT_DB || p_b) ? p_b - 64 * q : nullptr, d_b ? d_b + 64 * q : nullptr, P, s_pal);
+            }
+            if (s == 0) pkz_emit<WANT_DB>(omid, (!WANT_DB || o.pix) ? o.pix : nullptr, (WANT_DB && o.db) ? o.db + 1024 : nullptr, P, s_pal);
+        }
+        ++it;
+        if (!more) break;
+        cur = nxt;
+        // ---- the next frame: samples x window, stage 1
+        if (LD == PKZ_ASYNC) {
+            mbar_wait(bar, copies & 1u);
+            ++copies;
+        }
+        {
+            long long st;
+            const float* c0 = frame_ptr(cur, st);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) load_pair(v, j, c0, st);
+        }
+        if (LD == PKZ_ASYNC) __syncwarp(); // every lane has read its samples before the transpose overwrites them
+    }
+}
+
+} // namespace jade

@@ -22,14 +22,19 @@ struct jade_view {
     bool running = true;         // scroll mode (m_isRunning: the "Fix" button toggles it, Spectrogram.cpp:777-790)
     int64_t seen = 0;            // columns accounted for by earlier ticks
     bool first = true;           // the reference's first getMem reports "everything is new" (Spectrogram.cpp:18,236)
+    bool flip = true;            // engine rows: row 0 = highest bin (jade_config.flip_y); otherwise columns are turned over here
 };
 
 namespace {
 constexpr uint32_t kRed = 0xFFFF0000u; // juce::Colours::red
-inline void put_column(jade_view* v, int x, const uint32_t* col) // col[r], r = 0 is the top row
+// col[r] in the engine's row order; the image always has the lowest frequency at the bottom (y = H-1-hh, Spectrogram.cpp:642)
+inline void put_column(jade_view* v, int x, const uint32_t* col)
 {
     uint32_t* p = v->img.data() + x;
-    for (int r = 0; r < v->H; ++r) p[(size_t)r * v->W] = col[r];
+    if (v->flip)
+        for (int r = 0; r < v->H; ++r) p[(size_t)r * v->W] = col[r];
+    else
+        for (int r = 0; r < v->H; ++r) p[(size_t)(v->H - 1 - r) * v->W] = col[r];
 }
 inline void red_column(jade_view* v, int x)
 {
@@ -82,22 +87,30 @@ int jade_view_tick(jade_view* v, int* new_columns)
 {
     if (!v) return -1;
     int W = 0, H = 0, B = 0;
-    int64_t total = 0;
-    if (int r = jade_ring_info(v->e, &W, &H, &B, &total)) return r;
+    if (int r = jade_ring_info(v->e, &W, &H, &B, nullptr)) return r;
     if (W != v->W || H != v->H) { // Spectrogram.cpp:595-605: the image follows the data size
         v->W = W;
         v->H = H;
         v->img.assign((size_t)W * H, 0xFF000000u);
         v->cols.assign((size_t)W * H, 0u);
         v->recompute_all = true;
+        jade_config c;
+        if (int r = jade_get_config(v->e, &c)) return r;
+        v->flip = c.flip_y != 0;
     }
+    // ONE call both moves the fetch cursor and tells how many columns exist (first_col + n): the count and the columns
+    // cannot be separated by a concurrent jade_push_samples.  Columns older than a ring are dropped by the engine.
+    int n = 0;
+    int64_t first_col = 0;
+    if (int r = jade_fetch_columns(v->e, v->cols.data(), nullptr, W, &n, &first_col)) return r;
+    const int64_t total = first_col + n;
     if (total < v->seen) { // engine was reset / reconfigured
         v->seen = 0;
         v->first = true;
     }
     // m_newEntryCounter: columns since the previous tick; "everything" on the first one
     // (the reference's counter starts at int(100000000000) = 1215752192 and keeps counting, Spectrogram.cpp:18,112)
-    int64_t new_vals = v->first ? (int64_t)1215752192 + total : total - v->seen;
+    const int64_t new_vals = v->first ? (int64_t)1215752192 + total : total - v->seen;
     v->first = false;
     v->seen = total;
     const int pos = (int)(total % W); // ring write index (m_memCounter)
@@ -106,10 +119,7 @@ int jade_view_tick(jade_view* v, int* new_columns)
 
     if (v->recompute_all) { // :623-657
         v->recompute_all = false;
-        int n = 0;
-        int64_t first_col = 0;
-        if (int r = jade_fetch_columns(v->e, nullptr, nullptr, 0, &n, &first_col)) return r; // advance the fetch cursor
-        if (int r = jade_recolor_ring(v->e, v->cols.data())) return r;                        // [slot][row]
+        if (int r = jade_recolor_ring(v->e, v->cols.data())) return r; // [slot][row], includes the columns fetched above
         const int newwstart = W - pos;
         for (int ww = 0; ww < W; ++ww) {
             int neww = ww + newwstart;
@@ -119,20 +129,10 @@ int jade_view_tick(jade_view* v, int* new_columns)
         if (!v->running) red_column(v, pos % W);
         return 0;
     }
-    // :658-724 -- only the new columns
-    int n = 0;
-    int64_t first_col = 0;
-    if (new_vals > 0) {
-        if (int r = jade_fetch_columns(v->e, v->cols.data(), nullptr, (int)new_vals, &n, &first_col)) return r;
-        if (n != (int)new_vals) { // somebody else moved the fetch cursor: fall back to a full redraw next tick
-            v->recompute_all = true;
-            return jade_view_tick(v, nullptr);
-        }
-    }
+    // :658-724 -- only the new columns (n == new_vals here: new_vals <= W and the engine keeps a full ring)
     if (v->running) {
-        if (new_vals > 0 && new_vals < W)
-            for (int y = 0; y < H; ++y)
-                std::memmove(&v->img[(size_t)y * W], &v->img[(size_t)y * W + new_vals], (size_t)(W - new_vals) * 4);
+        if (n > 0 && n < W)
+            for (int y = 0; y < H; ++y) std::memmove(&v->img[(size_t)y * W], &v->img[(size_t)y * W + n], (size_t)(W - n) * 4);
         for (int i = 0; i < n; ++i) put_column(v, W - n + i, v->cols.data() + (size_t)i * H);
     } else {
         for (int i = 0; i < n; ++i) put_column(v, (int)((first_col + i) % W), v->cols.data() + (size_t)i * H);

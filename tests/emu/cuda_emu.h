@@ -9,6 +9,8 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <condition_variable>
+#include <mutex>
 #include <pthread.h>
 #include <thread>
 #include <vector>
@@ -24,6 +26,11 @@ struct BlockState {
     std::vector<char> smem;
     std::vector<float> mail; // one slot per thread: warp shuffles
     std::vector<unsigned long long> mail64;
+    // named barriers (PTX bar.sync / bar.arrive id, count): arrivals counted per id, a generation per completed barrier
+    std::mutex nb_mu;
+    std::condition_variable nb_cv;
+    unsigned nb_count[16] = {0};
+    unsigned long long nb_gen[16] = {0};
 };
 inline thread_local dim3 t_threadIdx, t_blockIdx;
 inline dim3 g_blockDim, g_gridDim;
@@ -38,6 +45,20 @@ inline void* dyn_smem() { return g_block->smem.data(); }
 
 inline void __syncthreads() { pthread_barrier_wait(&jade_emu::g_block->block_bar); }
 inline void __syncwarp(unsigned = 0xffffffffu) { pthread_barrier_wait(&jade_emu::g_block->warp_bar[threadIdx.x >> 5]); }
+// bar.arrive id, n: count this thread, do not wait.  bar.sync id, n: count this thread and wait until n threads have arrived.
+inline void jade_emu_named_bar(int id, unsigned n, bool wait)
+{
+    jade_emu::BlockState& st = *jade_emu::g_block;
+    std::unique_lock<std::mutex> lk(st.nb_mu);
+    const unsigned long long gen = st.nb_gen[id];
+    if (++st.nb_count[id] == n) {
+        st.nb_count[id] = 0;
+        ++st.nb_gen[id];
+        st.nb_cv.notify_all();
+        return;
+    }
+    if (wait) st.nb_cv.wait(lk, [&] { return st.nb_gen[id] != gen; });
+}
 inline float __shfl_xor_sync(unsigned, float v, int lane_mask)
 {
     jade_emu::BlockState& st = *jade_emu::g_block;

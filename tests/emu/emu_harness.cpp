@@ -7,6 +7,7 @@
 #include "../../jadespectrogram_b200/csrc/jade_pk.cuh"
 #include "../../jadespectrogram_b200/csrc/jade_pk_cta.cuh"
 #include "../../jadespectrogram_b200/csrc/jade_pk_small.cuh"
+#include "../../jadespectrogram_b200/csrc/jade_pkz.cuh"
 #include "../../jadespectrogram_b200/csrc/jade_host_tables.h"
 #include "../../include/jade_gpu.h"
 
@@ -47,10 +48,17 @@ void run_pk_one(const KParams& P, int npal, int grid)
 {
     const int block = (T == 32 ? jade::PkCfg::WARPS : jade::PkSmallCfg<(T == 32 ? 16 : T)>::WARPS) * 32;
     if constexpr (T == 32) {
-        // same routing as launch_stft: guard / cp.async staging (16-byte aligned) / LDG to registers (8-byte aligned)
-        // stereo kernel for AbsMean over two channels unless JADE_EMU_NOPAIR is set (tests cover both)
+        // same routing as launch_stft: AbsMean over two channels -> the one-complex-transform kernel (jade_pkz.cuh) for
+        // every column (TMA-staged when 16-byte aligned and interior, guarded otherwise) unless JADE_EMU_NOPAIR is set
+        // (JADE_EMU_PAIR2: the older two-real-transforms stereo kernel); else guard / cp.async staging / LDG to registers
         const bool pair_ok = MIXK == jade::MIX_SUM && P.channels == 2 && !getenv("JADE_EMU_NOPAIR");
-        if (GUARD) jade_emu::launch(jade::stft_pk2048_kernel<MIXK, WDB, jade::PK_LD_GUARD>, grid, block, jade::PkCfg::smem_bytes(npal), P);
+        const bool pair2 = getenv("JADE_EMU_PAIR2") != nullptr;
+        if (pair_ok && !pair2) {
+            const int zs = jade::PkzCfg::smem_bytes(npal), zb = jade::PkzCfg::WARPS * 32;
+            if (GUARD || !P.aligned4) jade_emu::launch(jade::stft_pkz2048_kernel<true, jade::PKZ_GUARD>, grid, zb, zs, P);
+            else jade_emu::launch(jade::stft_pkz2048_kernel<WDB, jade::PKZ_ASYNC>, grid, zb, zs, P);
+        }
+        else if (GUARD) jade_emu::launch(jade::stft_pk2048_kernel<MIXK, WDB, jade::PK_LD_GUARD>, grid, block, jade::PkCfg::smem_bytes(npal), P);
         else if (P.aligned4 && pair_ok)
             jade_emu::launch(jade::stft_pk2048x2_kernel<WDB>, grid, jade::PkPairCfg::WARPS * 32, jade::PkPairCfg::smem_bytes(npal), P);
         else if (P.aligned4) jade_emu::launch(jade::stft_pk2048_kernel<MIXK, WDB, jade::PK_LD_ASYNC>, grid, block, jade::PkCfg::smem_bytes(npal), P);
@@ -166,7 +174,7 @@ extern "C" int emu_render(const jade_config* cin, const int32_t* palette, int np
         long long lo = j0, hi = j1;
         while (lo < j1 && start(lo) < 0) ++lo;
         while (hi > lo && start(hi - 1) + N > nsamples) --hi;
-        if (!P.aligned2 || (T < 32 && !P.aligned4)) lo = hi = j0; // everything through the guarded instantiation
+        if (!P.aligned2 || (T < 32 && !P.aligned4) || getenv("JADE_EMU_FORCE_GUARD")) lo = hi = j0; // everything through the guarded instantiation
         auto sub = [&](long long a, long long b) {
             KParams Q = P;
             Q.first_col = a;

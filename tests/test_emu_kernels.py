@@ -45,15 +45,14 @@ def test_emulated_kernels_match_oracle(N, hop, ch, window, mix):
 
 
 @pytest.mark.parametrize("ch,mix", [(2, "absmean"), (1, "absmean"), (2, "right"), (4, "absmean")])
-@pytest.mark.parametrize("nopair", [False, True])
-def test_emulated_pk2048_pair_and_single(monkeypatch, ch, mix, nopair):
-    """N = 2048, TMA-staged interior frames: the stereo kernel (AbsMean over two channels: both per warp) and the
-    one-transform kernel (JADE_EMU_NOPAIR, and always for one or four contributing channels) against the oracle, and
-    bit-identical to each other."""
-    if nopair:
-        monkeypatch.setenv("JADE_EMU_NOPAIR", "1")
-    else:
-        monkeypatch.delenv("JADE_EMU_NOPAIR", raising=False)
+@pytest.mark.parametrize("variant", ["pair2", "single"])
+def test_emulated_pk2048_pair_and_single(monkeypatch, ch, mix, variant):
+    """N = 2048, TMA-staged interior frames: the two-real-transforms stereo kernel (JADE_EMU_PAIR2) and the one-transform
+    kernel (JADE_EMU_NOPAIR, and always for one or four contributing channels) against the oracle, and bit-identical to
+    each other."""
+    monkeypatch.delenv("JADE_EMU_NOPAIR", raising=False)
+    monkeypatch.delenv("JADE_EMU_PAIR2", raising=False)
+    monkeypatch.setenv("JADE_EMU_NOPAIR" if variant == "single" else "JADE_EMU_PAIR2", "1")
     N, hop, ncols = 2048, 512, 29
     x = signals.streams(2, ch, hop * (ncols - 1) + 64, 48000.0)
     pal = O.Palette(256, O.PAL["jade"]).table()
@@ -65,6 +64,32 @@ def test_emulated_pk2048_pair_and_single(monkeypatch, ch, mix, nopair):
     key = (ch, mix)
     prev = _PAIR_RESULTS.setdefault(key, (db, pix))
     assert np.array_equal(prev[0], db) and np.array_equal(prev[1], pix)
+
+
+@pytest.mark.parametrize("window", ["hann", "blackmanharris", "hannpoisson"])
+@pytest.mark.parametrize("want_db", [True, False])
+def test_emulated_pkz2048_complex_stereo(monkeypatch, window, want_db):
+    """N = 2048, AbsMean over two channels -- the product route: both channels as ONE 2048-point complex transform
+    (stft_pkz2048_kernel, |X_L|^2 + |X_R|^2 = (|Z[k]|^2 + |Z[N-k]|^2) / 2).  Against the oracle over a chain of frames per
+    warp (TMA staging of the next frame, rotated loop), and the TMA-staged instantiation bit-identical to the guarded one
+    (streaming == batch == sharded relies on it)."""
+    for k in ("JADE_EMU_NOPAIR", "JADE_EMU_PAIR2", "JADE_EMU_FORCE_GUARD"):
+        monkeypatch.delenv(k, raising=False)
+    N, hop, ncols = 2048, 512, 53
+    x = signals.streams(2, 2, hop * (ncols - 1) + 64, 48000.0, kind="mix")
+    x[1, 1] *= 1e-3  # a nearly silent right channel next to a loud left one
+    pal = O.Palette(256, O.PAL["jade"]).table()
+    db, pix = E.render(_cfg(N, hop, 2, window, "absmean"), pal, -50.0, 50.0, x, 0, ncols, N // 2 + 1, grid=1, want_db=want_db)
+    for s in range(x.shape[0]):
+        odb, opix = O.render_batch(x[s], fft_size=N, hop=hop, window=window, mix="absmean", ncols=ncols)
+        if want_db:
+            parity.check_db(db[s], odb, N, f"stream {s}")
+        parity.check_pixels(pix[s], opix, odb[:, ::-1], -50.0, 50.0, 256, f"stream {s}")
+    monkeypatch.setenv("JADE_EMU_FORCE_GUARD", "1")
+    gdb, gpix = E.render(_cfg(N, hop, 2, window, "absmean"), pal, -50.0, 50.0, x, 0, ncols, N // 2 + 1, grid=2, want_db=True)
+    assert np.array_equal(gpix, pix)
+    if want_db:
+        assert np.array_equal(gdb, db)
 
 
 _PAIR_RESULTS = {}
