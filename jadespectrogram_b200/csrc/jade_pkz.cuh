@@ -262,27 +262,28 @@ JADE_KERNEL(PkzCfg::WARPS * 32, 1) stft_pkz2048_kernel(const KParams P)
         }
     };
 
-    f2 v[64];
-    if (my_iters > 0) {
-        if (LD == PKZ_ASYNC) {
-            stage(cur);
-            mbar_wait(bar, copies & 1u);
-            ++copies;
-        }
-        long long st;
-        const float* c0 = frame_ptr(cur, st);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) load_pair(v, j, c0, st);
-        if (LD == PKZ_ASYNC) __syncwarp(); // every lane has read its samples before the transpose overwrites them
-    }
+    if (LD == PKZ_ASYNC && my_iters > 0) stage(cur);
 
     // eps = 1e-11 (Spectrogram.cpp:36) rides on the power FMAs: every output is the sum of one "low" power (register 0..15 of
     // a row, seeded with eps) and one "high" power (16..31, unseeded); lane 0 pairs row 0 with itself, so its DC and Nyquist
     // terms (register 0 / 16, added to themselves) carry eps / 2 each.
     const float eps = 1e-11f, eps0 = s == 0 ? 0.5e-11f : 1e-11f, eps16 = s == 0 ? 0.5e-11f : 0.0f;
 
-    for (unsigned it = 0; it < my_iters;) {
+    for (unsigned it = 0; it < my_iters; ++it) {
         const ColOut o = col_out(P, (int)cur.stream, P.first_col + cur.col);
+        // ---- samples x window, stage 1 (the frame was staged while the previous one was in pass 2)
+        f2 v[64];
+        if (LD == PKZ_ASYNC) {
+            mbar_wait(bar, copies & 1u);
+            ++copies;
+        }
+        {
+            long long st;
+            const float* c0 = frame_ptr(cur, st);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) load_pair(v, j, c0, st);
+        }
+        if (LD == PKZ_ASYNC) __syncwarp(); // every lane has read its samples before the transpose overwrites them
         fft64_pk_after_stage1(v); // v[k1] = Y[s, k1]
 #pragma unroll
         for (int k1 = 0; k1 < 64; ++k1) xw[k1 * Cfg::XROW + s] = v[k1];
@@ -306,6 +307,8 @@ JADE_KERNEL(PkzCfg::WARPS * 32, 1) stft_pkz2048_kernel(const KParams P)
         fft32_twisted(ub, trowb); // ub[k2] = Z[kb + 64 k2]
         // mean power of bin k (+ eps): |Z[k]|^2 + |Z[N-k]|^2.  Row s: bins s + 64 k2 mirror into row 64 - s at 31 - k2 (lane 0: row 0
         // at 32 - k2); row kb likewise into row s (lane 0: row 32 into itself).
+        // (the packed form -- (re_a^2 + re_b^2 + eps, im_a^2 + im_b^2) by two FFMA2, then one FADD -- issues one instruction
+        // less per output but was 3 % slower: the lane-0 selects become 64-bit, profiles/r02_pkz_variants.txt)
         float pa[32], pb[32];
 #pragma unroll
         for (int q = 0; q < 32; ++q) {
@@ -334,21 +337,7 @@ JADE_KERNEL(PkzCfg::WARPS * 32, 1) stft_pkz2048_kernel(const KParams P)
             }
             if (s == 0) pkz_emit<WANT_DB>(omid, (!WANT_DB || o.pix) ? o.pix : nullptr, (WANT_DB && o.db) ? o.db + 1024 : nullptr, P, s_pal);
         }
-        ++it;
-        if (!more) break;
         cur = nxt;
-        // ---- the next frame: samples x window, stage 1
-        if (LD == PKZ_ASYNC) {
-            mbar_wait(bar, copies & 1u);
-            ++copies;
-        }
-        {
-            long long st;
-            const float* c0 = frame_ptr(cur, st);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) load_pair(v, j, c0, st);
-        }
-        if (LD == PKZ_ASYNC) __syncwarp(); // every lane has read its samples before the transpose overwrites them
     }
 }
 
