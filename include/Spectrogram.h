@@ -12,14 +12,28 @@
  * plugin uses (preparetoProcess, setDesiredBlockSizeSamples, processBlock; PluginProcessor.cpp:108,148,
  * Spectrogram.cpp:164) and an empty juce::MidiBuffer stand in.
  *
+ * With JUCE present the header also carries what the reference's Spectrogram.h declares for the plugin shell and that
+ * PluginProcessor.{h,cpp} use: the four parameter descriptors (Spectrogram.h:22-58), `SpectrogramParameter`
+ * (Spectrogram.h:61-76, Spectrogram.cpp:793-832) and `Spectrogram::prepareParameter` (Spectrogram.h:113,
+ * Spectrogram.cpp:25-35, called at PluginProcessor.cpp:28).  `SpectrogramComponent` (Spectrogram.h:171-236, GUI) is NOT
+ * here: INTEGRATION.md section 1 says where it goes.
+ *
+ * Threading: one audio thread (processSynchronBlock) and one GUI thread (getMem, setters), as in the plugin.
+ * m_newEntryCounter is atomic; the structural setters (buildmem) hold m_protect, processSynchronBlock only try-locks it
+ * and drops the block while a rebuild is in progress (the rebuild clears all state anyway) -- the audio thread never
+ * waits for the GUI thread.
+ *
  * There is no CPU implementation behind this class: without a CUDA device every processing call returns -1 and
  * lastError() says why (the reference's int-status convention; no exceptions cross the audio thread).
  */
 #pragma once
 
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -34,6 +48,60 @@
 
 #if defined(JADE_HAVE_TGM_JUCE)
 #include "SynchronBlockProcessor.h"
+#if __has_include("PlugInGUISettings.h")
+#include "PlugInGUISettings.h" /* g_minColorVal / g_maxColorVal (PlugInGUISettings.h:37-38) */
+#define JADE_MIN_COLOR_VAL float(g_minColorVal)
+#define JADE_MAX_COLOR_VAL float(g_maxColorVal)
+#else
+#define JADE_MIN_COLOR_VAL (-50.0f)
+#define JADE_MAX_COLOR_VAL (50.0f)
+#endif
+
+/* Host-automatable display parameters of the plugin (Spectrogram.h:22-58): the frequency limits are stored as log(Hz), the
+ * colour limits in dB.  Same object names and fields as the reference, because the component code keeps using them. */
+struct JadeDisplayParamDesc
+{
+	std::string ID, name, unitName;
+	float minValue, maxValue, defaultValue;
+};
+inline const JadeDisplayParamDesc paramDisplayMinFreq{"MinFreq", "MinFreq", "Hz", std::log(1.f), std::log(10000.f), std::log(1.f)};
+inline const JadeDisplayParamDesc paramDisplayMaxFreq{"MaxFreq", "MaxFreq", "Hz", std::log(500.f), std::log(20000.f), std::log(20000.f)};
+inline const JadeDisplayParamDesc paramDisplayMinColor{"MinColor", "MinColor", "", JADE_MIN_COLOR_VAL, JADE_MAX_COLOR_VAL, JADE_MIN_COLOR_VAL};
+inline const JadeDisplayParamDesc paramDisplayMaxColor{"MaxColor", "MaxColor", "", JADE_MIN_COLOR_VAL, JADE_MAX_COLOR_VAL, JADE_MAX_COLOR_VAL};
+
+/* Spectrogram.h:61-76 / Spectrogram.cpp:793-832 */
+class SpectrogramParameter
+{
+public:
+	SpectrogramParameter() {}
+	/* appends the four AudioParameterFloat objects: frequencies shown as Hz with one decimal (stored value is log Hz),
+	 * colour limits as whole dB */
+	int addParameter(std::vector<std::unique_ptr<RangedAudioParameter>>& paramVector)
+	{
+		const JadeDisplayParamDesc* descs[4] = {&paramDisplayMinFreq, &paramDisplayMaxFreq, &paramDisplayMinColor, &paramDisplayMaxColor};
+		for (int i = 0; i < 4; ++i) {
+			const JadeDisplayParamDesc& d = *descs[i];
+			const bool isFreq = i < 2;
+			paramVector.push_back(std::make_unique<AudioParameterFloat>(
+				d.ID, d.name, NormalisableRange<float>(d.minValue, d.maxValue), d.defaultValue, d.unitName,
+				AudioProcessorParameter::genericParameter,
+				[isFreq](float value, int maxLen) {
+					return isFreq ? String(0.1 * int(std::exp(value) * 10 + 0.5), maxLen) : String(1.0 * int(value + 0.5), maxLen);
+				},
+				[](const String& text) { return text.getFloatValue(); }));
+		}
+		return 0;
+	}
+
+	std::atomic<float>* m_DisplayMinFreq = nullptr;
+	float m_DisplayMinFreqOld = 0.f;
+	std::atomic<float>* m_DisplayMaxFreq = nullptr;
+	float m_DisplayMaxFreqOld = 0.f;
+	std::atomic<float>* m_DisplayMinColor = nullptr;
+	float m_DisplayMinColorOld = 0.f;
+	std::atomic<float>* m_DisplayMaxColor = nullptr;
+	float m_DisplayMaxColorOld = 0.f;
+};
 #else
 namespace juce
 {
@@ -52,11 +120,13 @@ public:
 	void preparetoProcess(int channels, int maxBlockSize)
 	{
 		(void)maxBlockSize;
+		std::lock_guard<std::mutex> lk(m_accLock);
 		m_NrOfChannels = channels > 0 ? channels : 1;
 		resetAccumulator();
 	}
 	void setDesiredBlockSizeSamples(int n)
 	{
+		std::lock_guard<std::mutex> lk(m_accLock);
 		m_desired = n > 0 ? n : 1;
 		resetAccumulator();
 	}
@@ -65,6 +135,10 @@ public:
 	/* planar channel pointers, any numSamples */
 	int processBlock(const float* const* channelData, int numChannels, int numSamples, juce::MidiBuffer& midi)
 	{
+		/* the audio thread never waits: while the GUI thread resizes the accumulator the host block is dropped */
+		std::unique_lock<std::mutex> lk(m_accLock, std::try_to_lock);
+		if (!lk.owns_lock())
+			return 0;
 		int rc = 0;
 		int done = 0;
 		while (done < numSamples) {
@@ -104,6 +178,7 @@ protected:
 	int m_desired = 1024;
 	int m_fill = 0;
 	std::vector<std::vector<float>> m_acc;
+	std::mutex m_accLock; /* accumulator vs preparetoProcess / setDesiredBlockSizeSamples from another thread */
 };
 #endif
 
@@ -155,10 +230,29 @@ public:
 	Spectrogram(const Spectrogram&) = delete;
 	Spectrogram& operator=(const Spectrogram&) = delete;
 
+#if defined(JADE_HAVE_TGM_JUCE)
+	/* Spectrogram.cpp:25-35 (call site PluginProcessor.cpp:28): raw parameter pointers of the value tree state */
+	void prepareParameter(std::unique_ptr<AudioProcessorValueTreeState>& vts)
+	{
+		const JadeDisplayParamDesc* descs[4] = {&paramDisplayMinFreq, &paramDisplayMaxFreq, &paramDisplayMinColor, &paramDisplayMaxColor};
+		std::atomic<float>** raw[4] = {&m_SpecParameter.m_DisplayMinFreq, &m_SpecParameter.m_DisplayMaxFreq,
+									   &m_SpecParameter.m_DisplayMinColor, &m_SpecParameter.m_DisplayMaxColor};
+		float* old[4] = {&m_SpecParameter.m_DisplayMinFreqOld, &m_SpecParameter.m_DisplayMaxFreqOld,
+						 &m_SpecParameter.m_DisplayMinColorOld, &m_SpecParameter.m_DisplayMaxColorOld};
+		for (int i = 0; i < 4; ++i) {
+			*raw[i] = vts->getRawParameterValue(descs[i]->ID);
+			*old[i] = descs[i]->defaultValue;
+		}
+	}
+#endif
+
 	/* Spectrogram.cpp:37-135.  data[channel][fftsize]; returns 0 (the reference always does) or -1 on error. */
 	virtual int processSynchronBlock(std::vector<std::vector<float>>& data, juce::MidiBuffer& midiMessages)
 	{
 		(void)midiMessages;
+		std::unique_lock<std::mutex> lk(m_protect, std::try_to_lock);
+		if (!lk.owns_lock())
+			return 0; /* a structural setter is rebuilding the engine: this block is dropped, the rebuild clears all state */
 		if (!m_engine || !m_configured)
 			return -1;
 		if (data.size() < m_channels)
@@ -172,23 +266,26 @@ public:
 		if (jade_push_samples(m_engine, ptr, int(m_channels), int(m_fftsize)) != JADE_OK)
 			return setError(jade_last_error(m_engine));
 		if (!m_PauseMode) /* :111-118 */
-			m_newEntryCounter += m_feedblocks;
+			m_newEntryCounter.fetch_add(m_feedblocks, std::memory_order_release);
 		return 0;
 	}
 
 	// setter (Spectrogram.cpp:148-211)
 	void setSamplerate(float samplerate)
 	{
+		std::lock_guard<std::mutex> lk(m_protect);
 		m_fs = samplerate;
 		buildmem();
 	}
 	void setchannels(size_t newchannels)
 	{
+		std::lock_guard<std::mutex> lk(m_protect);
 		m_channels = newchannels;
 		buildmem();
 	}
 	void setFFTSize(size_t newFFTSize)
 	{
+		std::lock_guard<std::mutex> lk(m_protect); /* the reference's m_protect.enter(), Spectrogram.cpp:162 */
 		m_fftsize = newFFTSize;
 		setDesiredBlockSizeSamples(int(m_fftsize));
 		buildmem();
@@ -196,17 +293,20 @@ public:
 	}
 	void setclosestFFTSize_ms(float fftsize_ms)
 	{
+		std::lock_guard<std::mutex> lk(m_protect);
 		m_fftsize = getnextpowerof2(fftsize_ms);
 		setDesiredBlockSizeSamples(int(m_fftsize));
 		buildmem();
 	}
 	void setmemoryTime_s(float memsize_s)
 	{
+		std::lock_guard<std::mutex> lk(m_protect);
 		m_memsize_s = memsize_s;
 		buildmem();
 	}
 	void setfeed_percent(FeedPercentage feed)
 	{
+		std::lock_guard<std::mutex> lk(m_protect);
 		switch (feed) {
 		case FeedPercentage::perc100: m_feed_percent = 100; break;
 		case FeedPercentage::perc50: m_feed_percent = 50; break;
@@ -230,6 +330,7 @@ public:
 	/* extension: the reference fixes m_mode = AbsMean (Spectrogram.cpp:21) and has no setter */
 	void setMixMode(ChannelMixMode mode)
 	{
+		std::lock_guard<std::mutex> lk(m_protect);
 		m_mode = mode;
 		buildmem();
 	}
@@ -256,32 +357,35 @@ public:
 		const int W = m_memsize_blocks, B = int(m_freqsize);
 		if (mem.size() != size_t(W))
 			return -1;
-		int64_t total = 0;
-		jade_ring_info(m_engine, nullptr, nullptr, nullptr, &total);
-		if (size_t(m_newEntryCounter) >= mem.size()) {
+		/* The counter is read and cleared in ONE atomic step (the reference reads, uses and zeroes a plain int here,
+		 * Spectrogram.cpp:295-331).  WHICH columns are new is decided by the engine's own fetch cursor, so a block the audio
+		 * thread pushes between two statements of this function is neither lost nor delivered twice: it is either part of
+		 * this call or of the next one (a counter increment that arrives after its column was delivered only makes the next call
+		 * look, and find nothing). */
+		const int counted = m_newEntryCounter.exchange(0, std::memory_order_acq_rel);
+		int n = 0;
+		int64_t first = 0;
+		if (counted >= W) { /* :299-304 -- everything is new: the whole ring */
+			if (jade_fetch_columns(m_engine, nullptr, nullptr, 0, &n, &first) != JADE_OK) /* first mark everything as seen ... */
+				return setError(jade_last_error(m_engine));
 			m_scratch.resize(size_t(W) * B);
-			if (jade_read_ring_db(m_engine, m_scratch.data()) != JADE_OK)
+			if (jade_read_ring_db(m_engine, m_scratch.data()) != JADE_OK)                 /* ... then read at least that much */
 				return setError(jade_last_error(m_engine));
 			for (int kk = 0; kk < W; ++kk)
 				std::copy(m_scratch.begin() + size_t(kk) * B, m_scratch.begin() + size_t(kk + 1) * B, mem[size_t(kk)].begin());
-			int n = 0;
-			int64_t first = 0;
-			jade_fetch_columns(m_engine, nullptr, nullptr, 0, &n, &first); /* mark everything as seen */
-		} else if (m_newEntryCounter > 0) {
-			m_scratch.resize(size_t(m_newEntryCounter) * B);
-			int n = 0;
-			int64_t first = 0;
-			if (jade_fetch_columns(m_engine, nullptr, m_scratch.data(), m_newEntryCounter, &n, &first) != JADE_OK)
-				return setError(jade_last_error(m_engine));
-			for (int i = 0; i < n; ++i) {
-				const size_t slot = size_t((first + i) % W);
-				std::copy(m_scratch.begin() + size_t(i) * B, m_scratch.begin() + size_t(i + 1) * B, mem[slot].begin());
-			}
+			pos = int(first % W);
+			return counted;
 		}
-		const int newVals = m_newEntryCounter;
-		m_newEntryCounter = 0;
-		pos = int(total % W);
-		return newVals;
+		/* :305-320 -- the newest columns into their ring slots */
+		m_scratch.resize(size_t(W) * B);
+		if (jade_fetch_columns(m_engine, nullptr, m_scratch.data(), W, &n, &first) != JADE_OK)
+			return setError(jade_last_error(m_engine));
+		for (int i = 0; i < n; ++i) {
+			const size_t slot = size_t((first + i) % W);
+			std::copy(m_scratch.begin() + size_t(i) * B, m_scratch.begin() + size_t(i + 1) * B, mem[slot].begin());
+		}
+		pos = int((first + n) % W);
+		return n;
 	}
 
 	// ---- extensions over the reference ----
@@ -294,7 +398,7 @@ public:
 		int n = 0;
 		if (!m_engine || jade_fetch_columns(m_engine, pixels, nullptr, maxCols, &n, firstCol) != JADE_OK)
 			return -1;
-		m_newEntryCounter = 0;
+		m_newEntryCounter.store(0, std::memory_order_release);
 		return n;
 	}
 
@@ -358,7 +462,11 @@ private:
 	size_t m_fftsize = 1024;
 	ChannelMixMode m_mode = ChannelMixMode::AbsMean;
 	Windows m_windowChoice = Windows::Hann;
-	int m_newEntryCounter = kAllNew;
-	bool m_PauseMode = false;
+	std::atomic<int> m_newEntryCounter{kAllNew};
+	std::atomic<bool> m_PauseMode{false};
+	std::mutex m_protect; /* structural setters vs processSynchronBlock (the reference's CriticalSection, Spectrogram.h:133) */
+#if defined(JADE_HAVE_TGM_JUCE)
+	SpectrogramParameter m_SpecParameter; /* Spectrogram.h:165 */
+#endif
 	std::vector<float> m_scratch;
 };

@@ -1085,7 +1085,8 @@ int jade_push_samples(jade_engine* e, const float* const* planar, int nch, int n
             // earlier pushes of <= 8 columns each can still be in flight, so with W >= (kStageSlots + 1) * 8 the slots
             // zeroed here cannot be the target of a launch that is still running; otherwise fetch falls back to the event.
             // INVARIANT: every pixel format bakes a non-zero alpha byte (bake_pixel), so no complete pixel is ever 0.
-            if (n <= 8 && e->W >= (kStageSlots + 1) * 8) {
+            // A recolour kernel still in flight rewrites every slot (with the old columns), so nothing is armed behind one.
+            if (n <= 8 && e->W >= (kStageSlots + 1) * 8 && cudaEventQuery(e->ctl_ev) == cudaSuccess) {
                 uint32_t* ring = (uint32_t*)e->h_pixring.p;
                 for (long long i = 0; i < n; ++i) memset(ring + (size_t)((P.ring_col0 + i) % e->W) * e->R, 0, (size_t)e->R * 4);
             } else {

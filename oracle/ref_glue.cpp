@@ -157,6 +157,39 @@ int jr_view_width(void* v) { return static_cast<RefView*>(v)->comp.m_internalImg
 int jr_view_height(void* v) { return static_cast<RefView*>(v)->comp.m_internalImg.h; }
 const uint32_t* jr_view_pixels(void* v) { return static_cast<RefView*>(v)->comp.m_internalImg.px.data(); }
 
+/* The real SpectrogramComponent::paint (Spectrogram.cpp:432-545) against the recording Graphics stub.  Inputs: component size,
+ * scale factor and the two frequency sliders (log Hz).  Outputs: the source rectangle of the spectrogram blit (hStart,
+ * heightInterval: the crop maths :441-464), the 11 + 11 text boxes of the two axes (value parsed from the label the
+ * reference produced with the stub String, and the box's y) and the colourbar pixels.  Returns the colourbar height. */
+int jr_view_paint(void* v, int width, int height, float scale, float log_min_hz, float log_max_hz, int* crop /*[2]*/,
+                  float* tick_val /*[22]*/, int* tick_y /*[22]*/, uint32_t* colorbar, int colorbar_cap)
+{
+    RefView* r = static_cast<RefView*>(v);
+    r->comp.stubWidth = width;
+    r->comp.stubHeight = height;
+    r->comp.setScaleFactor(scale);
+    r->comp.m_DisplayMinFreqSlider.setValue(log_min_hz, dontSendNotification);
+    r->comp.m_DisplayMaxFreqSlider.setValue(log_max_hz, dontSendNotification);
+    Graphics g;
+    r->comp.paint(g);
+    if (g.images.size() < 2 || g.texts.size() < 22) return -1;
+    crop[0] = g.images[0].sy;
+    crop[1] = g.images[0].sh;
+    for (int i = 0; i < 22; ++i) {
+        std::string t = g.texts[size_t(i)].text;
+        float val = float(std::atof(t.c_str()));
+        if (!t.empty() && t.back() == 'k') val *= 1000.f;
+        tick_val[i] = val;
+        tick_y[i] = g.texts[size_t(i)].y;
+    }
+    const Graphics::ImageCall& cb = g.images[1];
+    const int n = cb.ih;
+    for (int i = 0; i < n && i < colorbar_cap; ++i) colorbar[i] = cb.px[size_t(i)];
+    return n;
+}
+float jr_view_min_display_freq(void* v) { return static_cast<RefView*>(v)->comp.m_minDisplayFreq; }
+float jr_view_max_display_freq(void* v) { return static_cast<RefView*>(v)->comp.m_maxDisplayFreq; }
+
 /* ---------------- timing: the reference's own classes on host threads ---------------- */
 /* Each thread owns one Spectrogram + one CColorPalette, configured in the plugin's order (PluginProcessor.cpp:108-112),
  * and runs its share of `nstreams` streams: processSynchronBlock per fft_size block, getMem, and per new column the

@@ -102,13 +102,22 @@ class MemoryBlock {};
 class XmlElement {};
 template <typename T> class AudioBuffer {};
 
+/* records what paint() draws (text boxes and image blits) so that the axis / colourbar arithmetic of the reference's own
+ * SpectrogramComponent::paint (Spectrogram.cpp:432-545) can be read back by oracle/ref_glue.cpp */
 class Graphics
 {
 public:
+    struct TextCall { std::string text; int x, y, w, h; };
+    struct ImageCall { int dx, dy, dw, dh, sx, sy, sw, sh, iw, ih; std::vector<uint32> px; };
     void fillAll(Colour) {}
-    void drawImage(const Image&, int, int, int, int, int, int, int, int, bool = false) {}
+    void drawImage(const Image& im, int dx, int dy, int dw, int dh, int sx, int sy, int sw, int sh, bool = false)
+    {
+        images.push_back(ImageCall{dx, dy, dw, dh, sx, sy, sw, sh, im.w, im.h, im.w <= 2 ? im.px : std::vector<uint32>()});
+    }
     void setFont(float) {}
-    void drawText(const String&, int, int, int, int, Justification, bool = true) {}
+    void drawText(const String& t, int x, int y, int w, int h, Justification, bool = true) { texts.push_back(TextCall{t.m, x, y, w, h}); }
+    std::vector<TextCall> texts;
+    std::vector<ImageCall> images;
 };
 
 class Component
@@ -120,8 +129,9 @@ public:
     void addAndMakeVisible(Component&) {}
     void addAndMakeVisible(Component*) {}
     LookAndFeel& getLookAndFeel() { static LookAndFeel l; return l; }
-    int getWidth() const { return 800; }
-    int getHeight() const { return 550; }
+    int getWidth() const { return stubWidth; }
+    int getHeight() const { return stubHeight; }
+    int stubWidth = 800, stubHeight = 550; /* the plugin's minimum editor size (PlugInGUISettings.h:3-5) */
     void repaint() {}
     void setBounds(int, int, int, int) {}
     void setVisible(bool) {}
