@@ -21,6 +21,7 @@
  *   getRGBColor | 0xFF000000 pixel loops (Spectrogram.cpp:623-724) fused into the kernels; jade_recolor_ring
  *   timerCallback image assembly    (Spectrogram.cpp:590-724)    jade_view_*
  *   paint() crop maths              (Spectrogram.cpp:441-459)    jade_linear_crop, jade_config.row_map
+ *   paint() axis ticks / colourbar  (Spectrogram.cpp:466-545)    jade_freq_axis_ticks, jade_color_axis_ticks, jade_colorbar
  *   (offline batch rendering, north star)                        jade_render_batch / jade_render_device
  */
 #ifndef JADE_GPU_H
@@ -122,6 +123,27 @@ int jade_get_value_range(jade_engine* e, float* mn, float* mx, float* mult);
 int jade_lookup_color(jade_engine* e, float value_db, int32_t* rgb);
 /* crop maths of SpectrogramComponent::paint (Spectrogram.cpp:441-459): bins [k_lo,k_hi) shown for fmin..fmax */
 int jade_linear_crop(float fs, int bins, float fmin, float fmax, int* k_lo, int* k_hi);
+/* ---- display arithmetic of SpectrogramComponent::paint (Spectrogram.cpp:432-545); host-only, no GPU needed ---- */
+/* slider clamp rules (:441-453): min >= fs/2 -> 0.9 fs/2; max >= fs/2 -> fs/2; min >= max -> 0.9 max */
+int jade_display_freq_clamp(float fs, float* min_hz, float* max_hz);
+typedef struct jade_axis_tick {
+    float value;    /* the rounded tick value the reference prints (Hz / dB) */
+    int32_t y;      /* top of its label box in component pixels */
+    char label[16]; /* text; the reference formats with juce::String(float), so only `value` is pinned */
+} jade_axis_tick;
+/* frequency axis (:466-503): nticks values from min_hz to max_hz, rounded to 1 / 10 / 100 Hz; comp_height = component
+ * height, scale = m_scaleFactor, menu_height = g_menuHeight (20), text_height = 20 in the reference */
+int jade_freq_axis_ticks(float min_hz, float max_hz, int comp_height, float scale, int menu_height, int text_height, int nticks,
+                         jade_axis_tick* out);
+/* colourbar axis (:524-545): tick values truncated to multiples of 10 between min_val and max_val (g_minColorVal / g_maxColorVal) */
+int jade_color_axis_ticks(float min_val, float max_val, int comp_height, float scale, int menu_height, int text_height, int nticks,
+                          jade_axis_tick* out);
+/* colourbar height in pixels (:510): int(comp_height - scale * menu_height) */
+int jade_colorbar_height(int comp_height, float scale, int menu_height);
+/* The colourbar itself (:511-521): out[y], y = 0 at the top, is the engine's current palette / value range applied to
+ * val = float(kk) / height * (ramp_max - ramp_min) + ramp_min at kk = height - 1 - y, in the engine's pixel format. */
+int jade_colorbar(jade_engine* e, int height, float ramp_min, float ramp_max, uint32_t* out);
+
 /* log max-pool band table (extension): lo/hi hold `rows` entries */
 int jade_log_rows(float fs, int fft_size, int rows, float fmin, float fmax, int32_t* lo, int32_t* hi);
 

@@ -33,6 +33,10 @@ class JadeConfig(C.Structure):
     ]
 
 
+class AxisTick(C.Structure):
+    _fields_ = [("value", C.c_float), ("y", C.c_int32), ("label", C.c_char * 16)]
+
+
 # every symbol include/jade_gpu.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 _PP = C.POINTER(C.c_void_p)
@@ -64,6 +68,11 @@ SYMBOLS = {
     "jade_get_value_range": (_I, [_P, _FP, _FP, _FP]),
     "jade_lookup_color": (_I, [_P, _F, C.POINTER(C.c_int32)]),
     "jade_linear_crop": (_I, [_F, _I, _F, _F, _IP, _IP]),
+    "jade_display_freq_clamp": (_I, [_F, _FP, _FP]),
+    "jade_freq_axis_ticks": (_I, [_F, _F, _I, _F, _I, _I, _I, _P]),
+    "jade_color_axis_ticks": (_I, [_F, _F, _I, _F, _I, _I, _I, _P]),
+    "jade_colorbar_height": (_I, [_I, _F, _I]),
+    "jade_colorbar": (_I, [_P, _I, _F, _F, _P]),
     "jade_log_rows": (_I, [_F, _I, _I, _F, _F, _P, _P]),
     "jade_push_samples": (_I, [_P, C.POINTER(_P), _I, _I]),
     "jade_fetch_columns": (_I, [_P, _P, _P, _I, _IP, C.POINTER(_I64)]),

@@ -985,6 +985,18 @@ int jade_lookup_color(jade_engine* e, float v, int32_t* rgb)
     return JADE_OK;
 }
 
+int jade_colorbar(jade_engine* e, int height, float ramp_min, float ramp_max, uint32_t* out)
+{
+    if (!e || !out || height < 1 || e->h_palette.empty()) return fail(e, JADE_ERR_ARG, "bad colourbar arguments");
+    std::lock_guard<std::mutex> lk(e->mu);
+    for (int kk = 0; kk < height; ++kk) { // Spectrogram.cpp:511-517
+        const float val = float(kk) / height * (ramp_max - ramp_min) + ramp_min;
+        const int32_t rgb = e->h_palette[jade_host::palette_index(val, e->range, (int)e->h_palette.size())];
+        out[height - 1 - kk] = bake_pixel(rgb, e->cfg.pixel_format);
+    }
+    return JADE_OK;
+}
+
 int jade_linear_crop(float fs, int bins, float fmin, float fmax, int* k_lo, int* k_hi)
 {
     if (!k_lo || !k_hi || bins < 1 || fs <= 0.f) return JADE_ERR_ARG;

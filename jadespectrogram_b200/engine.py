@@ -49,6 +49,29 @@ def default_config(**kw):
     return c
 
 
+def display_freq_clamp(fs, min_hz, max_hz):
+    """Slider clamp rules of SpectrogramComponent::paint (Spectrogram.cpp:441-453); host-only."""
+    a, b = C.c_float(min_hz), C.c_float(max_hz)
+    if _capi.load().jade_display_freq_clamp(float(fs), C.byref(a), C.byref(b)) != 0:
+        raise JadeError("bad arguments")
+    return a.value, b.value
+
+
+def axis_ticks(kind, lo, hi, comp_height=550, scale=1.0, menu_height=20, text_height=20, nticks=11):
+    """Tick values / label-box positions of the frequency ("freq") or colourbar ("color") axis (Spectrogram.cpp:466-545);
+    host-only.  Returns (values float32[nticks], y int32[nticks], labels)."""
+    lib = _capi.load()
+    t = (_capi.AxisTick * nticks)()
+    fn = lib.jade_freq_axis_ticks if kind == "freq" else lib.jade_color_axis_ticks
+    if fn(float(lo), float(hi), int(comp_height), float(scale), int(menu_height), int(text_height), int(nticks), t) != 0:
+        raise JadeError("bad arguments")
+    return (np.array([x.value for x in t], np.float32), np.array([x.y for x in t], np.int32), [x.label.decode() for x in t])
+
+
+def colorbar_height(comp_height=550, scale=1.0, menu_height=20):
+    return _capi.load().jade_colorbar_height(int(comp_height), float(scale), int(menu_height))
+
+
 class Engine:
     """One jade_engine (one GPU)."""
 
@@ -124,6 +147,12 @@ class Engine:
         a, b, m = C.c_float(), C.c_float(), C.c_float()
         self._ck(self.lib.jade_get_value_range(self.h, C.byref(a), C.byref(b), C.byref(m)))
         return a.value, b.value, m.value
+
+    def colorbar(self, height, ramp_min=-50.0, ramp_max=50.0):
+        """The colourbar column of SpectrogramComponent::paint (Spectrogram.cpp:511-521), top pixel first."""
+        out = np.empty(int(height), np.uint32)
+        self._ck(self.lib.jade_colorbar(self.h, int(height), float(ramp_min), float(ramp_max), out.ctypes.data))
+        return out
 
     def lookup_color(self, v):
         out = C.c_int32()

@@ -160,6 +160,13 @@ def _bind_ref_spec(L):
     L.jr_view_height.argtypes = [C.c_void_p]
     L.jr_view_pixels.argtypes = [C.c_void_p]
     L.jr_view_pixels.restype = C.POINTER(C.c_uint32)
+    if hasattr(L, "jr_view_paint"):
+        L.jr_view_paint.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.POINTER(C.c_int), f32p,
+                                    np.ctypeslib.ndpointer(np.int32, flags="C"), np.ctypeslib.ndpointer(np.uint32, flags="C"), C.c_int]
+        L.jr_view_min_display_freq.argtypes = [C.c_void_p]
+        L.jr_view_min_display_freq.restype = C.c_float
+        L.jr_view_max_display_freq.argtypes = [C.c_void_p]
+        L.jr_view_max_display_freq.restype = C.c_float
     L.jr_bench_batch.argtypes = [C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
                                  f32p, C.c_long, C.c_int, C.c_int, C.POINTER(C.c_long)]
     L.jr_bench_batch.restype = C.c_double
@@ -284,6 +291,24 @@ class View:
 
     def force_recompute(self):
         self._c("force_recompute")
+
+    def set_scheme(self, idx):
+        assert self.use_ref
+        self._c("set_scheme", int(idx))
+
+    def paint(self, width, height, scale, min_hz, max_hz):
+        """The reference's REAL SpectrogramComponent::paint (Spectrogram.cpp:432-545) on the recording Graphics stub:
+        dict(crop=(hStart, heightInterval), freq_val, freq_y, color_val, color_y, colorbar, min_hz, max_hz)."""
+        assert self.use_ref
+        crop = (C.c_int * 2)()
+        val = np.zeros(22, np.float32)
+        y = np.zeros(22, np.int32)
+        cb = np.zeros(4096, np.uint32)
+        n = self._c("paint", int(width), int(height), float(scale), float(np.log(np.float32(min_hz))),
+                    float(np.log(np.float32(max_hz))), crop, val, y, cb, cb.size)
+        assert n > 0, n
+        return dict(crop=(crop[0], crop[1]), freq_val=val[:11].copy(), freq_y=y[:11].copy(), color_val=val[11:].copy(),
+                    color_y=y[11:].copy(), colorbar=cb[:n].copy(), min_hz=self._c("min_display_freq"), max_hz=self._c("max_display_freq"))
 
     def image(self):
         h, w = self._c("height"), self._c("width")

@@ -89,3 +89,64 @@ def test_view_follows_reference_timer_callback(N, feed, ch):
     assert ticks > 6
     gv.close()
     eng.close()
+
+
+def test_colorbar_matches_the_reference_paint():
+    """jade_colorbar against the colourbar the REFERENCE's own paint() drew (Spectrogram.cpp:510-521; tests/golden/paint_ref.npz,
+    generated from oracle/_ref): ramp -50..+50 through the current scheme / value range, flipped, | 0xFF000000.  Bit exact."""
+    import pathlib
+
+    from jadespectrogram_b200 import engine as E
+    gold = np.load(pathlib.Path(__file__).parent / "golden" / "paint_ref.npz")
+    for i, case in enumerate(gold["cases"]):
+        h, scale, fs, N, scheme, mn, mx = int(case[1]), case[2], case[5], int(case[6]), int(case[7]), case[8], case[9]
+        eng = Engine(0, sample_rate=fs, fft_size=N, hop=N // 2, channels=2)
+        eng.set_palette_scheme(scheme, 256)
+        eng.set_value_range(mn, mx)
+        ref = gold[f"c{i}_colorbar"]
+        assert E.colorbar_height(h, scale) == len(ref)
+        assert np.array_equal(eng.colorbar(len(ref)), ref), f"case {i}"
+        eng.close()
+
+
+def test_view_on_unflipped_and_pooled_engines():
+    """The view keeps the reference's orientation (low frequency at the bottom, Spectrogram.cpp:642) whatever row order the
+    engine was configured with, and a full redraw works on log max-pool rows (jade_recolor_ring pools the stored dB values)."""
+    fs, N, hop = 48000.0, 1024, 512
+    x = signals.streams(1, 1, hop * 40, fs, kind="mix")[0]
+    imgs = {}
+    for flip in (1, 0):
+        eng = Engine(0, sample_rate=fs, fft_size=N, hop=hop, channels=1, ring_columns=32, flip_y=flip, row_map="linear_crop",
+                     fmin=0.0, fmax=24000.0)
+        v = View(eng)
+        v.tick()
+        for b in range(0, x.shape[1], hop):
+            eng.push(x[:, b:b + hop])
+            if (b // hop) % 7 == 6:
+                v.tick()
+        v.tick()
+        imgs[flip] = v.image()
+        v.close()
+        eng.close()
+    assert np.array_equal(imgs[0], imgs[1])
+    eng = Engine(0, sample_rate=fs, fft_size=N, hop=hop, channels=1, ring_columns=32, row_map="log_maxpool", rows=60, fmin=50.0, fmax=20000.0)
+    v = View(eng)
+    assert v.tick() > 0            # first tick = full redraw through jade_recolor_ring: used to fail on pooled rows
+    for b in range(0, hop * 10, hop):
+        eng.push(x[:, b:b + hop])
+    v.tick()
+    eng.set_value_range(-80.0, 10.0)
+    assert eng.lib.jade_view_invalidate(v.h) == 0
+    v.tick()
+    img = v.image()
+    assert img.shape == (60, 32) and (img >> 24 == 0xFF).all()
+    # the recoloured ring equals colouring the pooled dB values directly
+    pix = np.empty((32, 60), np.uint32)
+    assert eng.lib.jade_recolor_ring(eng.h, pix.ctypes.data) == 0
+    tot = C.c_int64(0)
+    assert eng.lib.jade_ring_info(eng.h, None, None, None, C.byref(tot)) == 0
+    total = int(tot.value)  # columns emitted so far (fewer than the ring holds: column c sits in slot c, newest on the right)
+    assert 0 < total < 32
+    assert np.array_equal(img[:, 32 - total:], pix[:total].T)
+    v.close()
+    eng.close()

@@ -12,7 +12,10 @@
                       oracle's float32 stand-in): window tables, dB rings after streaming seeded blocks through
                       processSynchronBlock/getMem for every feed percentage, and the assembled image.
 
-    python tools/gen_golden.py
+  paint_ref.npz    -- what the REFERENCE's own SpectrogramComponent::paint draws (crop rectangle of the spectrogram blit, the
+                      tick values / label boxes of both axes, the colourbar pixels) for a few sizes and slider positions.
+
+    python tools/gen_golden.py          (everything)      python tools/gen_golden.py paint   (paint_ref.npz only)
 """
 import hashlib
 import pathlib
@@ -151,8 +154,46 @@ def reference_class():
     print("spectrogram_ref.npz", len(out), "arrays")
 
 
+# (component width, height, m_scaleFactor, min Hz, max Hz, fs, FFT size, colour scheme, colour range)
+PAINT_CASES = [
+    (800, 550, 1.0, 1.0, 20000.0, 48000.0, 2048, 6, (-50.0, 50.0)),
+    (800, 550, 1.0, 100.0, 8000.0, 48000.0, 2048, 6, (-50.0, 50.0)),
+    (1100, 756, 1.375, 37.5, 12345.0, 44100.0, 1024, 4, (-30.0, 20.0)),
+    (1400, 962, 1.75, 500.0, 30000.0, 48000.0, 4096, 2, (-50.0, 0.0)),     # max above fs/2: clamped
+    (800, 550, 1.0, 9000.0, 600.0, 96000.0, 8192, 5, (10.0, -10.0)),        # min above max: 0.9 max
+    (937, 611, 1.17, 20.0, 149.0, 48000.0, 512, 1, (-80.0, -20.0)),        # ticks below the 150 Hz rounding rule
+]
+
+
+def paint_reference():
+    """The reference's own SpectrogramComponent::paint (oracle/_ref, recording Graphics stub): crop rectangle, axis ticks and
+    colourbar for a few component sizes / slider positions -> tests/golden/paint_ref.npz."""
+    assert O.have_ref_spec() and hasattr(O.ref(), "jr_view_paint"), "rebuild oracle/_ref (`make -C oracle`)"
+    out = {"cases": np.array([[c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7], c[8][0], c[8][1]] for c in PAINT_CASES], np.float64)}
+    for i, (w, h, scale, lo, hi, fs, N, scheme, rng) in enumerate(PAINT_CASES):
+        r = O.Spec(use_ref=True)
+        r.set_samplerate(fs)
+        r.set_memory_time_s(0.1)
+        r.set_fftsize(N)
+        view = O.View(r, use_ref=True)
+        view.set_scheme(scheme)
+        view.set_color_range(*rng)
+        view.tick()  # sizes the internal image (m_internalHeight = bins) and applies the colour range
+        p = view.paint(w, h, scale, lo, hi)
+        out[f"c{i}_crop"] = np.array(p["crop"], np.int32)
+        out[f"c{i}_hz"] = np.array([p["min_hz"], p["max_hz"]], np.float32)
+        for k in ("freq_val", "freq_y", "color_val", "color_y", "colorbar"):
+            out[f"c{i}_{k}"] = p[k]
+    np.savez_compressed(OUT / "paint_ref.npz", **out)
+    print("paint_ref.npz", len(out), "arrays")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "paint":
+        paint_reference()
+        sys.exit(0)
     palettes()
     windows()
     pipeline()
     reference_class()
+    paint_reference()
