@@ -3,15 +3,18 @@
 
 Workload (config.workload = "cfg2-batch"): BASELINE configs[1] geometry -- stereo 48 kHz, FFT 2048, hop 512, Hann,
 AbsMean mix, dB, Jade/256 palette over -50..+50 dB, one ARGB32 pixel per bin (1025 rows) -- applied to a batch of
-independent synthetic streams (noise*0.1 + sine sweep).  A "step" is one pass of the hot path over that batch.
+independent synthetic streams (noise*0.1 + sine sweep).  A "step" is `passes_per_step` passes of the hot path over that batch
+(>= 100 ms of kernels per step, so that the timed region lasts seconds and the clock record covers it).
 
   value   : frames/s with the inputs already resident in HBM (one main kernel launch + one for the boundary columns per
-            step, CUDA events, max over ranks)
+            pass, CUDA events, max over ranks)
   e2e     : frames/s through the reference-facing C ABI call jade_render_batch with pinned HOST buffers
             (H2D of the samples and D2H of the pixel columns inside the timed region)
   latency : per-block time of the real-time path (512-sample blocks, push + fetch through the C ABI, from a native C++
             caller -- tools/native/latency_probe -- with the Python loop's numbers beside it)
-  roofline: algorithmic bytes (4*hop*C + 4*R per frame) / kernel time against the measured HBM copy bandwidth
+  roofline: algorithmic bytes (4*hop*C + 4*R per frame) / kernel time against the measured HBM copy bandwidth; `secondary`
+            holds the on-chip limits beside it (FP32-pipe cycles and shared-memory wavefronts per frame from the committed
+            ncu profile x the measured frame rate / (SMs x SM clock)) -- SURVEY 8d: "report both"
   cpu_baseline: the CPU oracle port timed on this box's host cores on a bounded sample
 
 `--impl reference` times the reference's CPU implementation of the same path (oracle port / compiled reference).
@@ -37,8 +40,16 @@ CHANNELS = 2
 ROWS = N_FFT // 2 + 1
 BYTES_ALG = 4 * HOP * CHANNELS + 4 * ROWS  # 8196 B per frame (SURVEY 8d / BASELINE.md section 3)
 STREAM_SECONDS = 20.0
+STREAMS_PER_GPU = 256
 WORKLOAD = dict(workload="cfg2-batch", sample_rate=48000, fft_size=N_FFT, hop=HOP, channels=CHANNELS, window="hann",
                 mix="absmean", palette="jade256", range_db=[-50, 50], rows=ROWS, pixel="ARGB32")
+
+
+def workload_config(world):
+    """`config` of the JSON line: the workload only, identical for both arms (--impl ours / reference)."""
+    return dict(WORKLOAD, streams_per_gpu=STREAMS_PER_GPU, seconds_per_stream=STREAM_SECONDS,
+                l2_policy="inputs+outputs of one pass (2 x 1.97 GB per GPU) exceed L2 (126 MB) many times; no explicit flush",
+                parallelism=f"streams sharded over {world} GPU(s), no collective")
 
 
 def measured_peak():
@@ -170,10 +181,11 @@ def run_reference(args):
         total += frames
     dt = time.time() - t0
     fps = total / dt
-    sample = (f"each step = {per_step_streams} streams x 2.0 s of cfg2-batch ({frames} frames) on {threads} host threads; {what}")
+    sample = (f"bounded sample of the workload: each step = {per_step_streams} streams x 2.0 s of cfg2-batch ({frames} frames) on "
+              f"{threads} host threads (FFT plan cached per thread); {what}")
     line = dict(impl="reference", metric="stft_frames_per_sec", value=fps, unit="frames/s", n_gpus=args.gpus, steps=steps,
                 warmup=warm, ms_per_step=dt / steps * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None,
-                dtype="f32", data="synthetic", config=dict(WORKLOAD, streams_per_step=per_step_streams, seconds_per_stream=2.0),
+                dtype="f32", data="synthetic", config=workload_config(args.gpus),
                 cpu_baseline=dict(value=fps, unit="frames/s", cores=threads, kind=kind, sample=sample),
                 e2e=dict(value=fps, unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line))
@@ -232,8 +244,30 @@ def run_ours(args):
                      cuda_stream=stream)
     torch.cuda.synchronize()
 
-    def step():
+    def one_pass():
         eng.render_device(d_in.data_ptr(), S, nsamp, CHANNELS * nsamp, nsamp, 0, ncols, d_pix.data_ptr(), None, stream)
+
+    # passes per step: >= 100 ms of kernels per step (calibrated once, the same on every rank)
+    if args.passes > 0:
+        passes = args.passes
+    else:
+        for _ in range(3):
+            one_pass()
+        torch.cuda.synchronize()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(4):
+            one_pass()
+        c1.record()
+        torch.cuda.synchronize()
+        passes = max(1, int(-(-100.0 // (c0.elapsed_time(c1) / 4))))
+        passes = int(round(sharding.reduce_max(float(passes), dev)))
+    frames_pass = frames_step
+    frames_step = frames_pass * passes
+
+    def step():
+        for _ in range(passes):
+            one_pass()
 
     for _ in range(warm):
         step()
@@ -254,20 +288,34 @@ def run_ours(args):
     launches = eng.kernel_launches - l0
     total_ms = ev[0].elapsed_time(ev[steps])
     per_launch_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(steps)]
-    # keep the GPU busy a little longer so the clock sampler sees the load (untimed)
-    t_end = time.time() + 0.6
-    while rank == 0 and time.time() < t_end:
-        step()
-    torch.cuda.synchronize()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop() if rank == 0 else None  # sampled during the timed region only
     max_ms = sharding.reduce_max(total_ms, dev)  # the slowest rank defines the job time
     value = frames_step * steps * world / (max_ms * 1e-3)
-    kernel_ms = statistics.mean(per_launch_ms)
+    kernel_ms = statistics.mean(per_launch_ms) / passes  # one pass = the main kernel + the launch for the boundary columns
+
+    # ---- 1-GPU == N-GPU evidence on separate devices: rank 0 renders stream 0 of every other rank (same seed, same engine
+    # configuration) and compares a checksum of the pixel columns with the one that rank computed itself
+    shard_parity = None
+    if world > 1:
+        own = d_pix[0].to(torch.int64).sum().reshape(1)
+        sums = [torch.zeros_like(own) for _ in range(world)]
+        dist.all_gather(sums, own)
+        if rank == 0:
+            shard_parity = True
+            d_one = torch.empty((1, CHANNELS, nsamp), dtype=torch.float32, device=dev)
+            d_onepix = torch.empty((1, ncols, ROWS), dtype=torch.int32, device=dev)
+            for r in range(1, world):
+                eng.synth_device(d_one.data_ptr(), 1, CHANNELS, nsamp, CHANNELS * nsamp, nsamp, kind="mix", seed=20240601 + r,
+                                 cuda_stream=stream)
+                eng.render_device(d_one.data_ptr(), 1, nsamp, CHANNELS * nsamp, nsamp, 0, ncols, d_onepix.data_ptr(), None, stream)
+                torch.cuda.synchronize()
+                shard_parity = shard_parity and int(d_onepix[0].to(torch.int64).sum().item()) == int(sums[r].item())
 
     if args.only_kernel:  # short command for ncu captures: no e2e / latency / CPU legs
         if rank == 0:
             emit(dict(metric="stft_frames_per_sec", value=value, unit="frames/s", n_gpus=world, steps=steps,
-                      kernel_ms=kernel_ms, gpu_launches=int(launches), note="--only-kernel"))
+                      kernel_ms=kernel_ms, gpu_launches=int(launches), note="--only-kernel", passes_per_step=passes,
+                      config=dict(kernel=eng.kernel_name)))
         eng.close()
         return
 
@@ -339,12 +387,25 @@ def run_ours(args):
 
     if rank == 0:
         peak, peak_src = measured_peak()
-        achieved = BYTES_ALG * frames_step / (kernel_ms * 1e-3) / 1e9
-        traffic = None
+        achieved = BYTES_ALG * frames_pass / (kernel_ms * 1e-3) / 1e9
+        traffic, secondary = None, None
         tp = ROOT / "profiles" / "traffic.json"
         if tp.exists():
             try:
-                traffic = json.loads(tp.read_text()).get("cfg2-batch")
+                prof = json.loads(tp.read_text())
+                traffic = prof.get("cfg2-batch")
+                per = prof.get("cfg2-batch-per-frame")
+                if per:
+                    # on-chip limits beside the HBM one: cycles per frame from the committed ncu profile of this kernel, turned
+                    # into busy fractions with the frame rate and SM clock measured in THIS run
+                    clk = (clocks or {}).get("sm_mhz") or 1965.0
+                    fps_gpu = frames_pass / (kernel_ms * 1e-3)
+                    sm_cycles = props.multi_processor_count * clk * 1e6
+                    secondary = dict(fp32_pipe_frac=per["fp32_pipe_cycles"] * fps_gpu / sm_cycles,
+                                     smem_pipe_frac=per["smem_wavefronts"] * fps_gpu / sm_cycles,
+                                     issue_frac=per["warp_instructions"] / 4.0 * fps_gpu / sm_cycles,
+                                     per_frame=per, sm_mhz_used=clk,
+                                     note="per-frame counts from profiles/ (ncu), rate and clock from this run")
             except Exception:
                 traffic = None
         cpu = cpu_baseline(args.cpu_seconds) if not args.no_cpu else None
@@ -352,20 +413,30 @@ def run_ours(args):
             metric="stft_frames_per_sec", value=value, unit="frames/s", n_gpus=world, steps=steps, warmup=warm,
             ms_per_step=max_ms / steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
             data="synthetic (0.1*white noise + linear sine sweep per stream, generated on the device)",
-            config=dict(WORKLOAD, streams_per_gpu=S, seconds_per_stream=STREAM_SECONDS, frames_per_step_per_gpu=frames_step,
-                        input_bytes_per_step_per_gpu=int(d_in.numel() * 4), output_bytes_per_step_per_gpu=int(d_pix.numel() * 4),
-                        l2_policy="inputs+outputs per step exceed L2 (126 MB) many times; no explicit flush",
-                        parallelism=f"streams sharded over {world} GPU(s), no collective", kernel=eng.kernel_name),
-            e2e=e2e, gpu_launches=int(launches), clocks=clocks, latency=lat,
+            config=workload_config(world), kernel=eng.kernel_name,
+            run=dict(passes_per_step=passes, frames_per_pass_per_gpu=frames_pass, frames_per_step_per_gpu=frames_step,
+                     input_bytes_per_pass_per_gpu=int(d_in.numel() * 4), output_bytes_per_pass_per_gpu=int(d_pix.numel() * 4),
+                     timed_region_s=max_ms * 1e-3),
+            e2e=e2e, gpu_launches=int(launches), clocks=clocks, latency=lat, shard_parity=shard_parity,
             roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic,
-                          traffic_unit="DRAM bytes per launch (ncu dram__bytes_read+write, profiles/traffic.json)",
-                          algorithmic_bytes_per_launch=BYTES_ALG * frames_step,
-                          peak_source=peak_src, bytes_per_frame=BYTES_ALG, frames_per_launch=frames_step,
-                          kernel_ms=kernel_ms),
+                          traffic_unit="DRAM bytes per launch, from the committed ncu capture of this kernel (profiles/traffic.json), "
+                                       "not measured in this run",
+                          algorithmic_bytes_per_launch=BYTES_ALG * frames_pass,
+                          peak_source=peak_src, bytes_per_frame=BYTES_ALG, frames_per_launch=frames_pass,
+                          kernel_ms=kernel_ms, secondary=secondary),
             cpu_baseline=cpu)
         emit(line)
     if world > 1:
-        dist.barrier()
+        # The other ranks are done after the e2e reduction.  They wait for rank 0's latency and CPU legs on the HOST (a key in
+        # the rendezvous store), not in an NCCL barrier, which would keep their GPUs spinning for ~20 s.
+        try:
+            store = dist.distributed_c10d._get_default_store()
+            if rank == 0:
+                store.set("jade_bench_done", "1")
+            else:
+                store.wait(["jade_bench_done"])
+        except Exception:
+            pass
         dist.destroy_process_group()
     eng.close()
 
@@ -376,7 +447,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--streams", type=int, default=256, help="streams per GPU per step")
+    ap.add_argument("--streams", type=int, default=STREAMS_PER_GPU, help="streams per GPU per pass")
+    ap.add_argument("--passes", type=int, default=0, help="passes over the batch per step (0: calibrate to >= 100 ms per step)")
     ap.add_argument("--e2e-streams", type=int, default=128)
     ap.add_argument("--latency-blocks", type=int, default=2000)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)

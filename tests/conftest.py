@@ -11,6 +11,17 @@ sys.path.insert(0, str(ROOT / "tests"))
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with `-m gpu`)")
+    config.addinivalue_line("markers", "also_gpu: CPU-only test that is ALSO selected by `-m gpu`, so that the GPU run's record "
+                            "carries the oracle <-> compiled-reference pin (oracle/_ref travels to the GPU box prebuilt)")
+
+
+@pytest.hookimpl(tryfirst=True)
+def pytest_collection_modifyitems(config, items):
+    expr = (config.getoption("markexpr", "") or "").strip()
+    if expr == "gpu":  # the driver's GPU run: pull the also_gpu tests in
+        for it in items:
+            if it.get_closest_marker("also_gpu"):
+                it.add_marker(pytest.mark.gpu)
 
 
 @pytest.fixture(scope="session")

@@ -1,5 +1,6 @@
 """GPU tests of the drop-in C++ classes (include/Spectrogram.h, include/CColorpalette.h) driven exactly like the plugin
-drives the reference (PluginProcessor.cpp:102-114,148; Spectrogram.cpp:590-724), against the restated oracle class."""
+drives the reference (PluginProcessor.cpp:102-114,148; Spectrogram.cpp:590-724), against the restated oracle class AND against
+the reference's REAL class (oracle/_ref/libjade_ref.so: Spectrogram.cpp compiled in place; it travels to the GPU box prebuilt)."""
 import ctypes as C
 import pathlib
 
@@ -62,10 +63,14 @@ def _prepare(obj, fs, ch, N, feed, mem_s=1.0):
     obj.set_feed_percent(O.FEED[feed])
 
 
+ARMS = ["oracle", pytest.param("reference", marks=pytest.mark.skipif(not O.have_ref_spec(), reason="oracle/_ref not built"))]
+
+
+@pytest.mark.parametrize("arm", ARMS)
 @pytest.mark.parametrize("N,feed,ch", [(1024, "p50", 1), (2048, "p50", 2), (2048, "p25", 2), (2048, "p10", 1), (512, "p100", 2), (8192, "p25", 1)])
-def test_dropin_class_follows_reference_class(N, feed, ch):
+def test_dropin_class_follows_reference_class(N, feed, ch, arm):
     fs = 48000.0
-    d, o = Dropin(), O.Spec()
+    d, o = Dropin(), O.Spec(use_ref=(arm == "reference"))
     _prepare(d, fs, ch, N, feed)
     _prepare(o, fs, ch, N, feed)
     assert (d.spectrum_size(), d.memory_size(), d.samplerate()) == (o.spectrum_size(), o.memory_size(), o.samplerate())
@@ -91,9 +96,10 @@ def test_dropin_class_follows_reference_class(N, feed, ch):
     d.close()
 
 
-def test_pause_window_change_and_reblocker():
+@pytest.mark.parametrize("arm", ARMS)
+def test_pause_window_change_and_reblocker(arm):
     fs, N, ch = 48000.0, 1024, 2
-    d, o = Dropin(), O.Spec()
+    d, o = Dropin(), O.Spec(use_ref=(arm == "reference"))
     _prepare(d, fs, ch, N, "p50")
     _prepare(o, fs, ch, N, "p50")
     W, B = o.memory_size(), o.spectrum_size()

@@ -203,3 +203,41 @@ def test_block_emit_mode_matches_reference_counts(gpu_engine_factory, oracle):
             assert newv == 2
         parity.check_db(d, mem[[(pos - 2) % eng.W, (pos - 1) % eng.W]], N, f"block {b}")
         total += 2
+
+
+@pytest.mark.skipif(not __import__("oracle_lib").have_ref_spec(), reason="oracle/_ref (compiled reference) not built")
+@pytest.mark.parametrize("N,feed,ch,window", [(2048, 25, 2, "hann"), (1024, 50, 1, "hann"), (2048, 10, 2, "blackmanharris"),
+                                              (512, 100, 2, "hamming"), (4096, 25, 1, "flattop"), (2048, 50, 2, "hannpoisson")])
+def test_batch_matches_the_real_reference_class(gpu_engine_factory, oracle, N, feed, ch, window):
+    """jade_render_batch against the reference's REAL Spectrogram + CColorPalette (Spectrogram.cpp / CColorpalette.cpp compiled
+    in place into oracle/_ref/libjade_ref.so; only the FFT inside is the stand-in): the reference class is fed N-sample blocks
+    (processSynchronBlock, all four feed percentages incl. the non-uniform 10 % hop), its ring is read with getMem and coloured
+    with its own getRGBColor; the GPU renders the same samples in one batch call with the reference block geometry."""
+    fs, nblocks = FS, 14
+    x = signals.streams(1, ch, N * nblocks, fs, kind="mix")[0]
+    x *= 8.0
+    ref = oracle.Spec(use_ref=True)
+    ref.set_channels(ch)
+    ref.set_samplerate(fs)
+    ref.set_memory_time_s(30.0)  # a ring longer than the run: slot = column index
+    ref.set_fftsize(N)
+    ref.set_feed_percent(oracle.FEED[f"p{feed}"])
+    ref.set_window(oracle.WIN[window])
+    W, B = ref.memory_size(), ref.spectrum_size()
+    mem = np.zeros((W, B), np.float32)
+    ref.get_mem(mem)
+    for b in range(nblocks):
+        ref.process(x[:, b * N:(b + 1) * N])
+    newv, pos = ref.get_mem(mem)
+    ncols = nblocks * ref.feed_blocks()
+    assert newv == ncols == pos
+    rdb = mem[:ncols]
+    pal = oracle.Palette(256, oracle.PAL["jade"], use_ref=True)
+    pal.set_value_range(-50.0, 50.0)
+    rpix = (pal.lookup(rdb[:, ::-1].reshape(-1)).reshape(ncols, B).astype(np.uint32)) | np.uint32(0xFF000000)
+
+    eng = gpu_engine_factory(sample_rate=fs, fft_size=N, feed_percent=feed, channels=ch, window=window)
+    assert eng.columns_for(N * nblocks) == ncols
+    pix, db = eng.render_batch(x[None], want_db=True)
+    parity.check_db(db[0], rdb, N, "vs reference class")
+    parity.check_pixels(pix[0], rpix, rdb[:, ::-1], -50.0, 50.0, 256, "vs reference class")

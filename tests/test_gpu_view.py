@@ -1,6 +1,7 @@
 """GPU test of the display-image assembly (jade_view_*, include/jade_gpu.h) against the restated
 SpectrogramComponent::timerCallback of the oracle (itself pinned bit for bit against the reference's real one,
-tests/test_oracle_vs_reference.py): scroll mode, fixed mode with the red cursor, full redraws after a range change."""
+tests/test_oracle_vs_reference.py) and against the real one directly: scroll mode, fixed mode with the red cursor, full
+redraws after a range change."""
 import ctypes as C
 
 import numpy as np
@@ -48,21 +49,28 @@ def _compare(img, ref, table, label):
         assert np.abs(a - b).max() <= 1, f"{label}: palette indices differ by {np.abs(a - b).max()}"
 
 
+@pytest.mark.parametrize("arm", ["oracle", pytest.param("reference", marks=pytest.mark.skipif(not O.have_ref_spec(), reason="oracle/_ref not built"))])
 @pytest.mark.parametrize("N,feed,ch", [(1024, "p50", 2), (2048, "p25", 1), (512, "p100", 2)])
-def test_view_follows_reference_timer_callback(N, feed, ch):
+def test_view_follows_reference_timer_callback(N, feed, ch, arm):
+    """arm "reference": the comparand is the reference's REAL SpectrogramComponent::timerCallback on its REAL Spectrogram
+    (oracle/_ref, Spectrogram.cpp compiled in place), not the restatement."""
+    use_ref = arm == "reference"
     fs, mem_s = 48000.0, 0.5
     pct = {"p100": 100, "p50": 50, "p25": 25, "p10": 10}[feed]
     eng = Engine(0, sample_rate=fs, fft_size=N, channels=ch, feed_percent=pct, memory_time_s=mem_s, max_push=N)
     eng.set_palette_scheme("jade", 256)
     eng.set_value_range(-50.0, 50.0)
-    spec, pal = O.Spec(), O.Palette(256, O.PAL["jade"])
+    spec, pal = O.Spec(use_ref=use_ref), O.Palette(256, O.PAL["jade"])
     spec.set_channels(ch)
     spec.set_samplerate(fs)
     spec.set_memory_time_s(mem_s)
     spec.set_fftsize(N)
     spec.set_feed_percent(O.FEED[feed])
     table = pal.table()
-    ov, gv = O.View(spec, pal), View(eng)
+    ov, gv = (O.View(spec, use_ref=True) if use_ref else O.View(spec, pal)), View(eng)
+    if use_ref:
+        ov.set_scheme(O.PAL["jade"])      # the component's default scheme and range (Spectrogram.cpp:337,342)
+        ov.set_color_range(-50.0, 50.0)
     W = spec.memory_size()
     nblocks = 3 * W // spec.feed_blocks() + 5  # wraps the ring several times
     x = signals.streams(1, ch, N * nblocks, fs, kind="mix")[0]
@@ -83,7 +91,7 @@ def test_view_follows_reference_timer_callback(N, feed, ch):
             assert eng.lib.jade_view_set_running(gv.h, 1) == 0
         if b % 3 == 1 or b == nblocks - 1:
             no, ng = ov.tick(), gv.tick()
-            assert no == ng, (b, no, ng)
+            assert no is None or no == ng, (b, no, ng)  # the real timerCallback returns nothing; the restatement its newVals
             _compare(gv.image(), ov.image(), table, f"block {b}")
             ticks += 1
     assert ticks > 6

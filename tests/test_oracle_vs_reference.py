@@ -15,7 +15,9 @@ import pytest
 import oracle_lib as O
 import signals
 
-pytestmark = pytest.mark.skipif(not O.have_ref_spec(), reason="oracle/_ref/libjade_ref.so (compiled reference) not built")
+# also_gpu: CPU-only, but selected by the driver's `-m gpu` run too (tests/conftest.py), so that its record holds the whole pin
+pytestmark = [pytest.mark.skipif(not O.have_ref_spec(), reason="oracle/_ref/libjade_ref.so (compiled reference) not built"),
+              pytest.mark.also_gpu]
 
 FS = 48000.0
 
