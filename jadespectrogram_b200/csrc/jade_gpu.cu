@@ -26,6 +26,7 @@
 #include "jade_pk_cta.cuh"
 #include "jade_pk_small.cuh"
 #include "jade_pkz.cuh"
+#include "jade_pk_cluster.cuh"
 
 using jade::KParams;
 
@@ -43,7 +44,8 @@ struct KernelChoice {
     int blocks_per_sm = 1;
     int units_per_block = 1; // frames a block processes per loop iteration
     char name[32] = {0};
-    int family = 0; // 0 warp, 1 cta, 2 cta2
+    int family = 0; // 0 warp, 1 cta, 2 cta2, 3 packed warp kernels, 4 cluster of two CTAs per frame
+    int max_clusters = 0; // family 4: clusters that can be resident at once (cudaOccupancyMaxActiveClusters)
 };
 
 // Kernel instantiations live in their own translation units (jade_k_*.cu) so that they compile in parallel; each
@@ -55,7 +57,8 @@ typedef void (*kernel_fn)(const jade::KParams);
 kernel_fn warp_kernel(int T, int mixk, bool general);             // jade_k_warp_a.cu / jade_k_warp_b.cu
 kernel_fn cta_kernel(int R1, int mixk, bool general);             // jade_k_cta.cu
 kernel_fn pkcta_kernel(int R1, int mixk, bool want_db);           // jade_k_pkcta.cu
-kernel_fn pkcta2_kernel(int mixk);                                // jade_k_pkcta.cu
+kernel_fn pkcta2_kernel(int mixk);                                // jade_k_pkcta.cu (N = 65536 on one CTA; experiments)
+kernel_fn pkcl65536_kernel(int mixk);                             // jade_k_pkcl.cu (N = 65536 on a cluster of two CTAs)
 kernel_fn pk2048_kernel(int mixk, bool want_db, int load);        // jade_k_pk.cu (load = jade::PK_LD_*)
 kernel_fn pk2048x2_kernel(bool want_db);                           // jade_k_pk2.cu (stereo: two real transforms per warp; experiments)
 kernel_fn pkz2048_kernel(bool want_db, bool guard);                // jade_k_pkz.cu (stereo: one complex transform per frame)
@@ -368,11 +371,20 @@ int choose_kernel(jade_engine* e)
         if (!kc.fn) return fail(e, JADE_ERR_ARG, "unsupported fft_size %d", N);
         if (kc.fn_db) CU(e, cudaFuncSetAttribute((const void*)kc.fn_db, cudaFuncAttributeMaxDynamicSharedMemorySize, kc.smem));
     } else if (N == 65536) {
-        kc.family = 2;
+        static const bool one_cta = [] { const char* v = getenv("JADE_N65536"); return v && !strcmp(v, "cta2"); }(); // experiments
         kc.threads = 32 * 16;
-        snprintf(kc.name, sizeof kc.name, "pkcta2<16>");
-        kc.fn = jade_k::pkcta2_kernel(mu);
-        kc.smem = jade::PkCtaCfg<16>::smem_bytes2(e->npal, e->pooled ? e->R : 0);
+        if (one_cta) {
+            kc.family = 2;
+            snprintf(kc.name, sizeof kc.name, "pkcta2<16>");
+            kc.fn = jade_k::pkcta2_kernel(mu);
+            kc.smem = jade::PkCtaCfg<16>::smem_bytes2(e->npal, e->pooled ? e->R : 0);
+        } else {
+            // one frame per cluster of two CTAs: the two half-size transforms run on two SMs and meet through DSMEM
+            kc.family = 4;
+            snprintf(kc.name, sizeof kc.name, "pkcl65536");
+            kc.fn = jade_k::pkcl65536_kernel(mu);
+            kc.smem = jade::PkClCfg::smem_bytes(e->npal, e->pooled ? e->R : 0);
+        }
     } else {
         return fail(e, JADE_ERR_ARG, "unsupported fft_size %d (power of two in [64,65536])", N);
     }
@@ -384,6 +396,24 @@ int choose_kernel(jade_engine* e)
     CU(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)kc.fn, kc.threads, kc.smem));
     if (occ < 1) return fail(e, JADE_ERR_CUDA, "kernel %s does not fit on an SM (smem %d)", kc.name, kc.smem);
     kc.blocks_per_sm = occ;
+    if (kc.family == 4) {
+        // how many clusters fit at once (GPCs with an odd number of SMs leave one unpaired): the persistent grid is exactly that
+        cudaLaunchConfig_t lc = {};
+        lc.gridDim = dim3(2 * e->sm_count);
+        lc.blockDim = dim3(kc.threads);
+        lc.dynamicSmemBytes = (size_t)kc.smem;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        lc.attrs = at;
+        lc.numAttrs = 1;
+        int ncl = 0;
+        CU(e, cudaOccupancyMaxActiveClusters(&ncl, (const void*)kc.fn, &lc));
+        if (ncl < 1) return fail(e, JADE_ERR_CUDA, "kernel %s: no cluster of two CTAs fits (smem %d)", kc.name, kc.smem);
+        kc.max_clusters = ncl;
+    }
     e->kc = kc;
     return 0;
 }
@@ -455,6 +485,7 @@ void fill_params(jade_engine* e, KParams& P)
 // grid size: persistent, a multiple of the SM count when there is enough work
 int grid_for(jade_engine* e, const KernelChoice& kc, long long frames)
 {
+    if (kc.family == 4) return (int)(2 * std::max<long long>(1, std::min<long long>(frames, kc.max_clusters)));
     const long long blocks_needed = (frames + kc.units_per_block - 1) / kc.units_per_block;
     const long long cap = (long long)e->sm_count * kc.blocks_per_sm;
     return (int)std::max<long long>(1, std::min(blocks_needed, cap));

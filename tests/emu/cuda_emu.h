@@ -34,8 +34,16 @@ struct BlockState {
 };
 inline thread_local dim3 t_threadIdx, t_blockIdx;
 inline dim3 g_blockDim, g_gridDim;
-inline BlockState* g_block = nullptr;
+// the block a thread belongs to (thread-local: the two CTAs of a cluster run at the same time, launch_cluster)
+inline thread_local BlockState* g_block = nullptr;
 inline void* dyn_smem() { return g_block->smem.data(); }
+// thread-block cluster of two CTAs: rank of this CTA, the peer's state, one barrier over all threads of the cluster
+struct ClusterState {
+    BlockState* cta[2] = {nullptr, nullptr};
+    pthread_barrier_t bar;
+};
+inline thread_local ClusterState* t_cluster = nullptr;
+inline thread_local unsigned t_cluster_rank = 0;
 } // namespace jade_emu
 
 #define threadIdx jade_emu::t_threadIdx
@@ -102,11 +110,12 @@ void launch(K kernel, unsigned grid, unsigned block, size_t smem_bytes, A... arg
             unsigned cnt = (w + 1) * 32 <= block ? 32 : block - w * 32;
             pthread_barrier_init(&st.warp_bar[w], nullptr, cnt);
         }
-        g_block = &st;
+        BlockState* stp = &st;
         std::vector<std::thread> th;
         th.reserve(block);
         for (unsigned t = 0; t < block; ++t)
             th.emplace_back([=]() {
+                g_block = stp;
                 t_threadIdx = dim3(t);
                 t_blockIdx = dim3(b);
                 kernel(args...);
@@ -114,7 +123,57 @@ void launch(K kernel, unsigned grid, unsigned block, size_t smem_bytes, A... arg
         for (auto& x : th) x.join();
         pthread_barrier_destroy(&st.block_bar);
         for (auto& wb : st.warp_bar) pthread_barrier_destroy(&wb);
-        g_block = nullptr;
     }
+}
+
+// The same for kernels launched as clusters of two CTAs (__cluster_dims__(2)): the two blocks of a cluster run concurrently
+// and see each other's shared memory (cluster_peer_ptr) and a common barrier (cluster_sync).
+template <typename K, typename... A>
+void launch_cluster2(K kernel, unsigned grid, unsigned block, size_t smem_bytes, A... args)
+{
+    g_blockDim = dim3(block);
+    g_gridDim = dim3(grid);
+    for (unsigned c = 0; c + 1 < grid; c += 2) {
+        BlockState st[2];
+        ClusterState cl;
+        pthread_barrier_init(&cl.bar, nullptr, 2 * block);
+        const unsigned nw = (block + 31) / 32;
+        for (int r = 0; r < 2; ++r) {
+            st[r].smem.assign(smem_bytes + 64, 0);
+            st[r].mail.assign(block, 0.f);
+            st[r].mail64.assign(block, 0ull);
+            pthread_barrier_init(&st[r].block_bar, nullptr, block);
+            st[r].warp_bar.resize(nw);
+            for (unsigned w = 0; w < nw; ++w) pthread_barrier_init(&st[r].warp_bar[w], nullptr, (w + 1) * 32 <= block ? 32 : block - w * 32);
+            cl.cta[r] = &st[r];
+        }
+        ClusterState* clp = &cl;
+        std::vector<std::thread> th;
+        th.reserve(2 * block);
+        for (unsigned r = 0; r < 2; ++r)
+            for (unsigned t = 0; t < block; ++t)
+                th.emplace_back([=]() {
+                    g_block = clp->cta[r];
+                    t_cluster = clp;
+                    t_cluster_rank = r;
+                    t_threadIdx = dim3(t);
+                    t_blockIdx = dim3(c + r);
+                    kernel(args...);
+                });
+        for (auto& x : th) x.join();
+        for (int r = 0; r < 2; ++r) {
+            pthread_barrier_destroy(&st[r].block_bar);
+            for (auto& wb : st[r].warp_bar) pthread_barrier_destroy(&wb);
+        }
+        pthread_barrier_destroy(&cl.bar);
+    }
+}
+inline unsigned cluster_rank() { return t_cluster_rank; }
+inline void cluster_barrier() { pthread_barrier_wait(&t_cluster->bar); }
+// address of the peer CTA's copy of a shared-memory object of this CTA
+inline char* cluster_peer_ptr(const void* local, unsigned rank)
+{
+    const char* base = g_block->smem.data();
+    return t_cluster->cta[rank]->smem.data() + (static_cast<const char*>(local) - base);
 }
 } // namespace jade_emu

@@ -8,6 +8,7 @@
 #include "../../jadespectrogram_b200/csrc/jade_pk_cta.cuh"
 #include "../../jadespectrogram_b200/csrc/jade_pk_small.cuh"
 #include "../../jadespectrogram_b200/csrc/jade_pkz.cuh"
+#include "../../jadespectrogram_b200/csrc/jade_pk_cluster.cuh"
 #include "../../jadespectrogram_b200/csrc/jade_host_tables.h"
 #include "../../include/jade_gpu.h"
 
@@ -224,6 +225,14 @@ extern "C" int emu_render(const jade_config* cin, const int32_t* palette, int np
             sp.resize((size_t)grid * (N / 2 + 1));
             P.scratch_e = se.data();
             P.scratch_p = sp.data();
+            if (!getenv("JADE_EMU_CTA2")) { // the product route: a cluster of two CTAs per frame (jade_pk_cluster.cuh)
+                const int smem = jade::PkClCfg::smem_bytes(npal, pooled ? R : 0);
+                const unsigned cg = 2u * (unsigned)((grid + 1) / 2);
+                if (multi == jade::MIX_SEL) jade_emu::launch_cluster2(jade::stft_pkcl65536_kernel<jade::MIX_SEL>, cg, 512, smem, P);
+                else if (multi == jade::MIX_SUM) jade_emu::launch_cluster2(jade::stft_pkcl65536_kernel<jade::MIX_SUM>, cg, 512, smem, P);
+                else jade_emu::launch_cluster2(jade::stft_pkcl65536_kernel<jade::MIX_NONE>, cg, 512, smem, P);
+                return R;
+            }
             const int smem = jade::PkCtaCfg<16>::smem_bytes2(npal, pooled ? R : 0);
             if (multi == jade::MIX_SEL) jade_emu::launch(jade::stft_pkcta2_kernel<16, jade::MIX_SEL>, grid, 512, smem, P);
             else if (multi == jade::MIX_SUM) jade_emu::launch(jade::stft_pkcta2_kernel<16, jade::MIX_SUM>, grid, 512, smem, P);

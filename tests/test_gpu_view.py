@@ -35,8 +35,16 @@ class View:
         self.lib.jade_view_destroy(self.h)
 
 
-def _compare(img, ref, table, label):
+def _compare(img, ref, table, label, wrapped_cursor_differs=False):
     assert img.shape == ref.shape, (label, img.shape, ref.shape)
+    if wrapped_cursor_differs:
+        # The real timerCallback only wraps the cursor column that lands exactly on W (Spectrogram.cpp:715-716); columns
+        # W+1.. are written out of bounds there (the stub Image drops them).  The product and the restatement wrap them
+        # (DESIGN.md): every red pixel of the reference must be red here, and the extra red ones sit in the first columns.
+        assert (img[ref == RED] == RED).all(), f"{label}: red cursor differs"
+        extra = (img == RED) & (ref != RED)
+        assert not extra[:, 3:].any(), f"{label}: unexpected red pixels"
+        ref = np.where(extra, RED, ref).astype(ref.dtype)
     assert np.array_equal(img == RED, ref == RED), f"{label}: red cursor differs"
     diff = img != ref
     # colours come from float32 spectra that differ in the last bits: a few pixels may sit on the other side of a palette
@@ -92,7 +100,7 @@ def test_view_follows_reference_timer_callback(N, feed, ch, arm):
         if b % 3 == 1 or b == nblocks - 1:
             no, ng = ov.tick(), gv.tick()
             assert no is None or no == ng, (b, no, ng)  # the real timerCallback returns nothing; the restatement its newVals
-            _compare(gv.image(), ov.image(), table, f"block {b}")
+            _compare(gv.image(), ov.image(), table, f"block {b}", wrapped_cursor_differs=use_ref)
             ticks += 1
     assert ticks > 6
     gv.close()
