@@ -5,4 +5,5 @@ include/Spectrogram.h / include/CColorpalette.h.  This package is the Python mir
 tests and the benchmark.  There is no CPU fallback: without the built CUDA library the package raises.
 """
 from ._capi import JadeConfig, load  # noqa: F401
-from .engine import Engine, JadeError, default_config, host_alloc, host_free  # noqa: F401
+from .engine import (Engine, JadeError, default_config, device_count, host_alloc, host_free,  # noqa: F401
+                     render_batch_multi)

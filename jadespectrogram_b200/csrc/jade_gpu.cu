@@ -108,7 +108,17 @@ struct PinBuf {
 };
 
 constexpr int kStageSlots = 8;
-constexpr int kPipe = 3; // batch pipeline depth
+constexpr int kPipe = 6; // batch pipeline slots allocated; jade_render_batch uses pipe_depth() of them
+// pipeline depth in use: 3 (H2D, kernel and D2H of consecutive chunks overlap); JADE_PIPE_DEPTH = 2..6 for experiments
+inline int pipe_depth()
+{
+    static const int d = [] {
+        const char* v = getenv("JADE_PIPE_DEPTH");
+        const int n = v ? atoi(v) : 3;
+        return n < 2 ? 2 : (n > kPipe ? kPipe : n);
+    }();
+    return d;
+}
 
 } // namespace
 
@@ -116,7 +126,7 @@ struct jade_engine {
     int device = 0;
     int sm_count = 148;
     cudaStream_t stream = nullptr;
-    cudaStream_t pipe_stream[kPipe] = {nullptr, nullptr, nullptr};
+    cudaStream_t pipe_stream[kPipe] = {};
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
     bool timed = false;
     std::string err;
@@ -1354,7 +1364,8 @@ int jade_render_batch(jade_engine* e, const float* samples, int nstreams, int64_
         streams_per_chunk = std::max<long long>(1, std::min<long long>(nstreams, (long long)(budget / ((size_t)ncols * col_bytes))));
     }
     int slot = 0;
-    bool used[kPipe] = {false, false, false};
+    bool used[kPipe] = {};
+    const int depth = pipe_depth();
     struct Pending {
         bool active = false;
         uint32_t* dst_pix = nullptr;
@@ -1454,7 +1465,7 @@ int jade_render_batch(jade_engine* e, const float* samples, int nstreams, int64_
                 pend[slot].pix_bytes = pix_bytes;
                 pend[slot].db_bytes = db_bytes;
             }
-            slot = (slot + 1) % kPipe;
+            slot = (slot + 1) % depth;
         }
     }
     for (int s = 0; s < kPipe; ++s)

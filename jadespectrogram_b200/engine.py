@@ -248,6 +248,31 @@ class Engine:
 _PINNED = {}
 
 
+def device_count():
+    """CUDA devices visible to libjade_gpu.so (0 without a GPU)."""
+    return int(_capi.load().jade_device_count())
+
+
+def render_batch_multi(engines, samples, first_col=0, ncols=None, want_pix=True, want_db=False):
+    """jade_render_batch_multi: one identically configured engine per GPU; streams are range-partitioned (a single stream:
+    its columns, each GPU re-reading the N - hop input halo), no inter-GPU exchange.  Returns (pixels, db) like render_batch."""
+    samples = np.ascontiguousarray(samples, np.float32)
+    if samples.ndim == 2:
+        samples = samples[None]
+    ns, ch, n = samples.shape
+    e0 = engines[0]
+    if ncols is None:
+        ncols = e0.columns_for(n) - first_col
+    pix = np.empty((ns, ncols, e0.R), np.uint32) if want_pix else None
+    db = np.empty((ns, ncols, e0.B), np.float32) if want_db else None
+    arr = (C.c_void_p * len(engines))(*[e.h for e in engines])
+    rc = e0.lib.jade_render_batch_multi(arr, len(engines), samples.ctypes.data, ns, n, int(first_col), int(ncols),
+                                        pix.ctypes.data if pix is not None else None, db.ctypes.data if db is not None else None)
+    if rc != 0:
+        raise JadeError(f"jade_render_batch_multi failed ({rc}): {e0.lib.jade_last_error(None).decode()}")
+    return pix, db
+
+
 def host_alloc(shape, dtype):
     """numpy array backed by page-locked memory from jade_host_alloc; release it with host_free(arr)."""
     lib = _capi.load()
