@@ -51,8 +51,9 @@ JADE_DEVICE f2 rowget(const f2* rowbuf, int k)
 
 // M = 1024 R1 point complex FFT by the whole CTA.  ld(m, x, w) yields the raw sample pair and the window pair of
 // complex point m (the product is formed here, fused with stage 1).  Result in rowbuf (see rowget).
+// wa = W_M^t of this thread (P.twA[1024 + t], loaded once per kernel): column n2 = t + 32 R1 c needs W_M^n2 = wa W_32^c.
 template <int R1, typename Loader>
-JADE_DEVICE void cta_fft_pk(f2* rowbuf, const f2* s_twI, const cpx* JADE_RESTRICT twA, Loader ld)
+JADE_DEVICE void cta_fft_pk(f2* rowbuf, const f2* s_twI, f2 wa, Loader ld)
 {
     using Cfg = PkCtaCfg<R1>;
     constexpr int RS = Cfg::RS, CPT = 32 / R1, H = R1 / 2;
@@ -69,13 +70,11 @@ JADE_DEVICE void cta_fft_pk(f2* rowbuf, const f2* s_twI, const cpx* JADE_RESTRIC
             win_stage1<R1>(a, j, xa, wa, xb, wb);
         }
         fft_pk_after_stage1<R1>(a);
-        // twiddles W_M^(n2 k1), k1 = 1 .. R1-1: one table value (k1 = 1) per column, the others by squaring / one more
-        // product (depth <= log2 R1, a few ulp) -- R1 - 2 fewer L2 round trips per column in a latency-bound kernel
+        // twiddles W_M^(n2 k1), k1 = 1 .. R1-1: k1 = 1 is the thread's base value times a compile-time 32nd root of unity
+        // (no table read: the 8 bytes per column and frame used to come from L2, 64 KB per frame at N = 16384), the others
+        // by squaring / one more product (depth <= log2 R1, a few ulp)
         f2 wk[R1];
-        {
-            const cpx w = twA[1024 + n2];
-            wk[1] = pk(w.x, w.y);
-        }
+        wk[1] = c == 0 ? wa : cmul2(wa, pk(cos32(c & 15), -sin32(c & 15)));
 #pragma unroll
         for (int k1 = 2; k1 < R1; ++k1) wk[k1] = (k1 & 1) ? cmul2(wk[k1 - 1], wk[1]) : cmul2(wk[k1 / 2], wk[k1 / 2]);
         rowbuf[n2] = a[0];
@@ -146,6 +145,14 @@ JADE_KERNEL(32 * R1, PkCtaCfg<R1>::MINB) stft_pkcta_kernel(const KParams P)
     if (MIXK == MIX_NONE) ch1 = ch0 + 1;
     const f2* JADE_RESTRICT winp = reinterpret_cast<const f2*>(P.window);
     const float scale = (MIXK == MIX_SUM) ? (1.0f / (float)P.channels) : 1.0f;
+    // per-thread twiddle bases, loaded once: W_M^t (column pass) and W_N^t (real-FFT split); every other twiddle of this thread
+    // is one of them times a compile-time root of unity (they used to be two 8-byte L2 reads per point and frame)
+    f2 wa, ws;
+    {
+        const cpx a = P.twA[1024 + t], b = P.twP[t];
+        wa = pk(a.x, a.y);
+        ws = pk(b.x, b.y);
+    }
 
     // Interior frames on a multiple of 4 samples (P.aligned4) are STAGED: the TMA engine copies the frame's R1 rows of
     // 1024 complex samples into the row matrix (cp.async.bulk, one mbarrier completion) while the CTA is still in the
@@ -193,18 +200,18 @@ JADE_KERNEL(32 * R1, PkCtaCfg<R1>::MINB) stft_pkcta_kernel(const KParams P)
             if (staged) {
                 mbar_wait(bar, copies & 1u);
                 ++copies;
-                cta_fft_pk<R1>(rowbuf, s_twI, P.twA, [&](int m, f2& xv, f2& wv) {
+                cta_fft_pk<R1>(rowbuf, s_twI, wa, [&](int m, f2& xv, f2& wv) {
                     xv = rowbuf[(m >> 10) * Cfg::RS + (m & 1023)]; // the thread's own column: replaced in place below
                     wv = winp[m];
                 });
             } else if (fast) {
                 const f2* xz = reinterpret_cast<const f2*>(x + st);
-                cta_fft_pk<R1>(rowbuf, s_twI, P.twA, [&](int m, f2& xv, f2& wv) {
+                cta_fft_pk<R1>(rowbuf, s_twI, wa, [&](int m, f2& xv, f2& wv) {
                     xv = xz[m];
                     wv = winp[m];
                 });
             } else {
-                cta_fft_pk<R1>(rowbuf, s_twI, P.twA, [&](int m, f2& xv, f2& wv) {
+                cta_fft_pk<R1>(rowbuf, s_twI, wa, [&](int m, f2& xv, f2& wv) {
                     const cpx z = load_pair_guarded(x, st + 2 * m, ns);
                     xv = pk(z.x, z.y);
                     wv = winp[m];
@@ -215,10 +222,10 @@ JADE_KERNEL(32 * R1, PkCtaCfg<R1>::MINB) stft_pkcta_kernel(const KParams P)
                 const int k = t + THREADS * q;
                 const f2 zk = rowget<R1>(rowbuf, k);
                 const f2 zp = rowget<R1>(rowbuf, (M - k) & (M - 1));
-                const cpx w = P.twP[k]; // W_N^k ; -i W_N^k = (w.y, -w.x)
+                const f2 w = cmul2(ws, pk(cos64(q), -sin64(q))); // W_N^k = W_N^t W_64^q ; -i W_N^k = (w.y, -w.x)
                 const f2 A = add2(zk, conj2(zp));
                 const f2 Bv = sub2(zk, conj2(zp));
-                const f2 T = cmul2(Bv, pk(w.y, -w.x));
+                const f2 T = cmul2(Bv, pk(hi(w), -lo(w)));
                 const f2 xp = add2(A, T), xm = sub2(A, T);
                 alo[q] = fm(lo(xp), lo(xp), fm(hi(xp), hi(xp), alo[q]));
                 ahi[q] = fm(lo(xm), lo(xm), fm(hi(xm), hi(xm), ahi[q]));
@@ -291,6 +298,11 @@ JADE_KERNEL(32 * R1, 1) stft_pkcta2_kernel(const KParams P)
     __syncthreads();
     grid_dep_wait();
 
+    f2 wa;
+    {
+        const cpx a = P.twA[1024 + t];
+        wa = pk(a.x, a.y);
+    }
     f2* se = reinterpret_cast<f2*>(P.scratch_e) + (long long)blockIdx.x * (M2 + 1);
     float* sp = P.scratch_p + (long long)blockIdx.x * (NH + 1);
     const unsigned total = (unsigned)P.ncols * (unsigned)P.nstreams;
@@ -315,25 +327,25 @@ JADE_KERNEL(32 * R1, 1) stft_pkcta2_kernel(const KParams P)
                     const float4* x4 = reinterpret_cast<const float4*>(xs);
                     const float4* w4 = reinterpret_cast<const float4*>(win);
                     if (half == 0) {
-                        cta_fft_pk<R1>(rowbuf, s_twI, P.twA, [&](int m, f2& xv, f2& wv) {
+                        cta_fft_pk<R1>(rowbuf, s_twI, wa, [&](int m, f2& xv, f2& wv) {
                             const float4 a = x4[m], w = w4[m];
                             xv = pk(a.x, a.z);
                             wv = pk(w.x, w.z);
                         });
                     } else {
-                        cta_fft_pk<R1>(rowbuf, s_twI, P.twA, [&](int m, f2& xv, f2& wv) {
+                        cta_fft_pk<R1>(rowbuf, s_twI, wa, [&](int m, f2& xv, f2& wv) {
                             const float4 a = x4[m], w = w4[m];
                             xv = pk(a.y, a.w);
                             wv = pk(w.y, w.w);
                         });
                     }
                 } else if (fast) {
-                    cta_fft_pk<R1>(rowbuf, s_twI, P.twA, [&](int m, f2& xv, f2& wv) {
+                    cta_fft_pk<R1>(rowbuf, s_twI, wa, [&](int m, f2& xv, f2& wv) {
                         xv = pk(xs[4 * m + half], xs[4 * m + 2 + half]);
                         wv = pk(win[4 * m + half], win[4 * m + 2 + half]);
                     });
                 } else {
-                    cta_fft_pk<R1>(rowbuf, s_twI, P.twA, [&](int m, f2& xv, f2& wv) {
+                    cta_fft_pk<R1>(rowbuf, s_twI, wa, [&](int m, f2& xv, f2& wv) {
                         const long long i0 = st + 4LL * m + half, i1 = i0 + 2;
                         const long long c0 = i0 < 0 ? 0 : (i0 < ns ? i0 : ns - 1), c1 = i1 < 0 ? 0 : (i1 < ns ? i1 : ns - 1);
                         const float a = x[c0], b = x[c1]; // clamped address, value selected afterwards: no branches

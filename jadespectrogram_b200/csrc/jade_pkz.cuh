@@ -30,29 +30,6 @@
 
 namespace jade {
 
-// cos(2 pi m / 64), m = 0..16
-JADE_HD constexpr float cos64_q(int m)
-{
-    return m == 0 ? 1.0f
-         : m == 1 ? 0.99518472667219692873f
-         : m == 2 ? 0.98078528040323043058f
-         : m == 3 ? 0.95694033573220882438f
-         : m == 4 ? 0.92387953251128673848f
-         : m == 5 ? 0.88192126434835504956f
-         : m == 6 ? 0.83146961230254523567f
-         : m == 7 ? 0.77301045336273699338f
-         : m == 8 ? 0.70710678118654757274f
-         : m == 9 ? 0.63439328416364548779f
-         : m == 10 ? 0.55557023301960228867f
-         : m == 11 ? 0.47139673682599780857f
-         : m == 12 ? 0.38268343236508983729f
-         : m == 13 ? 0.29028467725446233105f
-         : m == 14 ? 0.19509032201612833135f
-         : m == 15 ? 0.09801714032956077016f
-                   : 0.0f;
-}
-JADE_HD constexpr float cos64(int m) { return m <= 16 ? cos64_q(m) : -cos64_q(32 - m); }
-JADE_HD constexpr float sin64(int m) { return m <= 16 ? cos64_q(16 - m) : cos64_q(m - 16); }
 JADE_HD constexpr int brev6(int v) { return (brev5(v & 31) << 1) | (v >> 5); }
 
 // radix-2 DIT butterfly with W = exp(-2 pi i M64/64), M64 in [0, 32)
