@@ -39,6 +39,7 @@ typedef void (*kernel_fn)(const KParams);
 struct KernelChoice {
     kernel_fn fn = nullptr;
     kernel_fn fn_db = nullptr; // variant that also stores the float dB column (only where the two differ)
+    kernel_fn fn_run = nullptr, fn_run_db = nullptr; // variant for long runs of evenly spaced columns with hop = N/4 (pkz2048: PKZ_RING)
     int threads = 0;
     int smem = 0;
     int blocks_per_sm = 1;
@@ -62,6 +63,7 @@ kernel_fn pkcl65536_kernel(int mixk);                             // jade_k_pkcl
 kernel_fn pk2048_kernel(int mixk, bool want_db, int load);        // jade_k_pk.cu (load = jade::PK_LD_*)
 kernel_fn pk2048x2_kernel(bool want_db);                           // jade_k_pk2.cu (stereo: two real transforms per warp; experiments)
 kernel_fn pkz2048_kernel(bool want_db, bool guard);                // jade_k_pkz.cu (stereo: one complex transform per frame)
+kernel_fn pkz2048_run_kernel(bool want_db);
 kernel_fn pksmall_kernel(int T, int mixk, bool want_db, bool guard); // jade_k_pksmall_a.cu / _b.cu
 } // namespace jade_k
 namespace {
@@ -319,12 +321,18 @@ int choose_kernel(jade_engine* e)
                     kp.fn = jade_k::pkz2048_kernel(false, false);
                     kp.fn_db = jade_k::pkz2048_kernel(true, false);
                     ke = kp;
+                    kp.fn_run = jade_k::pkz2048_run_kernel(false);
+                    kp.fn_run_db = jade_k::pkz2048_run_kernel(true);
                     snprintf(ke.name, sizeof ke.name, "pkz2048-guard");
                     ke.fn = jade_k::pkz2048_kernel(true, true);
                     e->has_mid = false; // 8- but not 16-byte aligned frames: the guarded instantiation
                 }
                 CU(e, cudaFuncSetAttribute((const void*)kp.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.smem));
                 CU(e, cudaFuncSetAttribute((const void*)kp.fn_db, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.smem));
+                if (kp.fn_run) {
+                    CU(e, cudaFuncSetAttribute((const void*)kp.fn_run, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.smem));
+                    CU(e, cudaFuncSetAttribute((const void*)kp.fn_run_db, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.smem));
+                }
                 int occ_p = 0;
                 CU(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_p, (const void*)kp.fn, kp.threads, kp.smem));
                 if (occ_p < 1) return fail(e, JADE_ERR_CUDA, "kernel %s does not fit on an SM (smem %d)", kp.name, kp.smem);
@@ -513,7 +521,12 @@ int launch_one(jade_engine* e, const KernelChoice& kc, KParams& P, cudaStream_t 
             return fail(e, JADE_ERR_STATE, "scratch not sized for grid %d", grid);
     }
     void* args[] = {(void*)&P};
-    const kernel_fn fn = (P.db && kc.fn_db) ? kc.fn_db : kc.fn;
+    kernel_fn fn = (P.db && kc.fn_db) ? kc.fn_db : kc.fn;
+    // long runs of evenly spaced columns, a quarter frame apart: the instantiation that walks contiguous columns per warp
+    static const bool no_run = [] { const char* v = getenv("JADE_PK_LOAD"); return v && !strcmp(v, "norun"); }(); // experiments
+    if (kc.fn_run && !no_run && P.hop * 4 == P.N && (P.fb == 1 ? P.bstride == P.hop : P.bstride == P.fb * P.hop) &&
+        frames >= 16ll * grid * kc.units_per_block)
+        fn = P.db ? kc.fn_run_db : kc.fn_run;
     if (P.ring_w > 0) {
         // streaming push: programmatic dependent launch behind ingest_kernel (every STFT kernel calls grid_dep_wait()
         // after its table prologue, jade_kernels.cuh)

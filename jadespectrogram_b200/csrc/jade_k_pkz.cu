@@ -10,4 +10,10 @@ kernel_fn pkz2048_kernel(bool want_db, bool guard)
     if (guard) return want_db ? (kernel_fn)stft_pkz2048_kernel<true, PKZ_GUARD> : (kernel_fn)stft_pkz2048_kernel<false, PKZ_GUARD>;
     return want_db ? (kernel_fn)stft_pkz2048_kernel<true, PKZ_ASYNC> : (kernel_fn)stft_pkz2048_kernel<false, PKZ_ASYNC>;
 }
+// long runs of evenly spaced columns (hop = N/4): contiguous columns per warp, samples kept in a tensor-memory ring
+kernel_fn pkz2048_run_kernel(bool want_db)
+{
+    using namespace jade;
+    return want_db ? (kernel_fn)stft_pkz2048_kernel<true, PKZ_RING> : (kernel_fn)stft_pkz2048_kernel<false, PKZ_RING>;
+}
 } // namespace jade_k

@@ -27,6 +27,12 @@
 // and sharded renderings agree bit for bit.
 #pragma once
 #include "jade_pk.cuh"
+#include "jade_tmem.cuh"
+
+// JADE_PKZ_TMEM = 1: the per-lane window and twisted-twiddle tables live in tensor memory (jade_tmem.cuh) instead of shared memory
+#ifndef JADE_PKZ_TMEM
+#define JADE_PKZ_TMEM 1
+#endif
 
 namespace jade {
 
@@ -99,6 +105,41 @@ JADE_HD int twz_exponent(int k1, int t)
 // second row of lane l
 JADE_HD int pkz_row_b(int l) { return l == 0 ? 32 : 64 - l; }
 
+// the twisted pass in two halves with the table held in registers (raw words of f2 entries t = 0..7, then 8..15)
+JADE_DEVICE float u2f(uint32_t u)
+{
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+JADE_DEVICE uint32_t f2u(float f)
+{
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    return u;
+}
+JADE_DEVICE void fft32_twisted_lo(f2* u, const uint32_t* r)
+{
+    f2 w[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) w[i] = pk(u2f(r[2 * i]), u2f(r[2 * i + 1]));
+    tw_blocks<2, 0>(u, w);
+    tw_blocks<4, 0>(u, w + 1);
+    tw_blocks<8, 0>(u, w + 2);
+    tw_blocks<16, 0>(u, w + 4);
+}
+JADE_DEVICE void fft32_twisted_hi(f2* u, const uint32_t* r)
+{
+    f2x2 t[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        t[i].a = pk(u2f(r[4 * i]), u2f(r[4 * i + 1]));
+        t[i].b = pk(u2f(r[4 * i + 2]), u2f(r[4 * i + 3]));
+    }
+    tw32_half<0>(u, t[0], t[1]);
+    tw32_half<4>(u, t[2], t[3]);
+}
+
 struct PkzCfg {
     static constexpr int N = 2048, B = 1025;
 #ifndef JADE_PKZ_WARPS
@@ -110,16 +151,24 @@ struct PkzCfg {
     static constexpr int XROW = 34;   // f2 words per transpose row
     static constexpr int XCH = 64 * XROW; // f2 words per warp buffer (17 408 B): transpose, and landing area of the next frame
     static constexpr int CH1 = 32 * XROW; // f2 offset of channel 1's 8 KB inside the buffer
+    static constexpr bool TM = JADE_PKZ_TMEM != 0;
+    static constexpr int TM_COLS = 512; // tensor-memory columns: 0..31 twisted table of row a, 32..63 of row b, 64..127 window; 128 (1 + warp / 4) ..: that warp's
+                                        // sample ring (the warps w, w + 4, w + 8 share the 32 lanes of quadrant w % 4)
+    static_assert(WARPS <= 12, "one 128-column sample ring per warp of a quadrant");
     static constexpr int off_win = 0;
-    static constexpr int off_twa = off_win + 32 * WROW * 4;
-    static constexpr int off_twb = off_twa + 32 * TROW * 8;
-    static constexpr int off_pal = off_twb + 32 * TROW * 8;
+    static constexpr int off_twa = off_win + (TM ? 0 : 32 * WROW * 4);
+    static constexpr int off_twb = off_twa + (TM ? 0 : 32 * TROW * 8);
+    static constexpr int off_pal = off_twb + (TM ? 0 : 32 * TROW * 8);
     static JADE_HD int off_bar(int npal) { return off_pal + ((npal + 1) * 4 + 15) / 16 * 16; } // table + the `>= m_Max` entry
-    static JADE_HD int off_xch(int npal) { return off_bar(npal) + (WARPS * 8 + 15) / 16 * 16; }
+    static JADE_HD int off_xch(int npal) { return off_bar(npal) + (WARPS * 8 + 8 + 15) / 16 * 16; } // mbarriers + the TMEM address
     static JADE_HD int smem_bytes(int npal) { return off_xch(npal) + WARPS * XCH * 8; }
 };
 
-enum { PKZ_ASYNC = 0, PKZ_GUARD = 1 };
+// PKZ_ASYNC: interior aligned frames staged by the TMA engine, frames dealt round-robin to the warps;  PKZ_GUARD: bounds-checked
+// global loads;  PKZ_RING: TMA-staged like PKZ_ASYNC, but every warp takes a contiguous run of columns and keeps the frame's
+// samples in a ring of four 512-sample chunks in tensor memory, so that a frame whose start lies one chunk after its
+// predecessor's reads only its NEW chunk from shared memory (evenly spaced columns with hop = N/4, the batch renderer's case).
+enum { PKZ_ASYNC = 0, PKZ_GUARD = 1, PKZ_RING = 2 };
 
 // Epilogue of one bin (cf. emit_bin): p already carries the reference's + 1e-11 (Spectrogram.cpp:36,107).  lg = log2 p; dB value
 // (optional) = 3.0103 lg; palette index = trunc(lg ck1 + ck0) clamped to [0, npal] by ONE integer min/max, where entry
@@ -165,6 +214,8 @@ JADE_KERNEL(PkzCfg::WARPS * 32, 1) stft_pkz2048_kernel(const KParams P)
 {
     using Cfg = PkzCfg;
     constexpr int WARPS = Cfg::WARPS;
+    constexpr bool STAGED = LD != PKZ_GUARD, RING = LD == PKZ_RING;
+    static_assert(!RING || Cfg::TM, "the sample ring lives in tensor memory");
     JADE_DYN_SMEM(smem);
     char* sm = reinterpret_cast<char*>(smem);
     float* s_win = reinterpret_cast<float*>(sm + Cfg::off_win);
@@ -175,17 +226,54 @@ JADE_KERNEL(PkzCfg::WARPS * 32, 1) stft_pkz2048_kernel(const KParams P)
     f2* s_xch = reinterpret_cast<f2*>(sm + Cfg::off_xch(P.npal));
 
     // ---- per-lane tables
-    for (int i = threadIdx.x; i < Cfg::N; i += blockDim.x) s_win[(i & 31) * Cfg::WROW + (i >> 5)] = P.window[i]; // n = s + 32 n1
-    if (LD == PKZ_ASYNC && threadIdx.x < WARPS) mbar_init(s_bar + threadIdx.x, 1);
-    for (int i = threadIdx.x; i < 512; i += blockDim.x) {
-        const int l = i & 31, t = i >> 5;
-        const cpx a = P.twP[twz_exponent(l, t)]; // W_2048^e, e < 1024
-        s_twa[l * Cfg::TROW + t] = pk(a.x, a.y);
-        const cpx b = P.twP[twz_exponent(pkz_row_b(l), t)];
-        s_twb[l * Cfg::TROW + t] = pk(b.x, b.y);
-    }
+    if (STAGED && threadIdx.x < WARPS) mbar_init(s_bar + threadIdx.x, 1);
     for (int i = threadIdx.x; i <= P.npal; i += blockDim.x) s_pal[i] = P.palette[i < P.npal ? i : P.ci_hi];
+    uint32_t tq = 0; // tensor-memory address of this warp's quadrant of the tables
+    if constexpr (Cfg::TM) {
+        uint32_t* s_tm = reinterpret_cast<uint32_t*>(s_bar + WARPS);
+        const int l = threadIdx.x & 31;
+        if (threadIdx.x < 32) tm_alloc(s_tm, Cfg::TM_COLS);
+        tm_fence_before_sync();
+        __syncthreads();
+        tm_fence_after_sync();
+        tq = tm_quadrant_base(*s_tm);
+        if (threadIdx.x < 128) { // warp q fills quadrant q: thread l writes lane 32 q + l
+            uint32_t r[16];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { // columns 16 c ..: entries t = 8 (c & 1) .. + 7 of row a (c < 2) / row b
+                const int k1 = c < 2 ? l : pkz_row_b(l);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const cpx a = P.twP[twz_exponent(k1, 8 * (c & 1) + i)]; // W_2048^e, e < 1024
+                    r[2 * i] = f2u(a.x);
+                    r[2 * i + 1] = f2u(a.y);
+                }
+                tm_st<16>(tq + 16 * c, r);
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { // columns 64 + 16 c ..: window of n1 = 8 c .. + 7, then of n1 = 32 + 8 c .. + 7 (n = l + 32 n1)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    r[i] = f2u(P.window[l + 32 * (8 * c + i)]);
+                    r[8 + i] = f2u(P.window[l + 32 * (32 + 8 * c + i)]);
+                }
+                tm_st<16>(tq + 64 + 16 * c, r);
+            }
+            tm_wait_st();
+        }
+        tm_fence_before_sync();
+    } else {
+        for (int i = threadIdx.x; i < Cfg::N; i += blockDim.x) s_win[(i & 31) * Cfg::WROW + (i >> 5)] = P.window[i]; // n = s + 32 n1
+        for (int i = threadIdx.x; i < 512; i += blockDim.x) {
+            const int l = i & 31, t = i >> 5;
+            const cpx a = P.twP[twz_exponent(l, t)]; // W_2048^e, e < 1024
+            s_twa[l * Cfg::TROW + t] = pk(a.x, a.y);
+            const cpx b = P.twP[twz_exponent(pkz_row_b(l), t)];
+            s_twb[l * Cfg::TROW + t] = pk(b.x, b.y);
+        }
+    }
     __syncthreads();
+    if constexpr (Cfg::TM) tm_fence_after_sync();
     grid_dep_wait();
 
     const int s = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -204,32 +292,40 @@ JADE_KERNEL(PkzCfg::WARPS * 32, 1) stft_pkz2048_kernel(const KParams P)
     const unsigned total = (unsigned)P.ncols * (unsigned)P.nstreams;
     const unsigned gstep = gridDim.x * WARPS;
     const unsigned g0 = blockIdx.x * WARPS; // the CTA's first frame
-    if (g0 >= total) return;                // (CTA-uniform)
-    unsigned g = g0 + warp;
-    const unsigned my_iters = g < total ? (total - g + gstep - 1) / gstep : 0; // frames of this warp
+    if (!Cfg::TM && g0 >= total) return;    // (CTA-uniform; with tensor memory allocated the CTA runs on to the release at the end)
+    unsigned g = g0 + warp, my_iters; // first frame and number of frames of this warp
     PkzWalk cur, nxt;
-    cur.init(g < total ? g : 0u, gstep, (unsigned)P.ncols);
+    if (RING) { // a contiguous run of columns per warp
+        const unsigned per = (total + gstep - 1) / gstep;
+        const unsigned b = min(total, g * per), e = min(total, b + per);
+        my_iters = e - b;
+        cur.init(b < total ? b : 0u, 1u, (unsigned)P.ncols);
+    } else {
+        my_iters = g < total ? (total - g + gstep - 1) / gstep : 0;
+        cur.init(g < total ? g : 0u, gstep, (unsigned)P.ncols);
+    }
     nxt = cur;
 
     auto frame_ptr = [&](const PkzWalk& u, long long& st) { // channel 0 of the frame; st = its first sample index (may be < 0)
         st = frame_start(P, P.first_col + u.col);
         return P.samples + (long long)u.stream * P.stream_stride;
     };
-    auto stage = [&](const PkzWalk& u) { // both channels of a frame -> the warp buffer (lane 0, after a __syncwarp())
+    // both channels of a frame -> the warp buffer (lane 0, after a __syncwarp()); last_chunk: only its last 512 samples, in place
+    auto stage = [&](const PkzWalk& u, bool last_chunk = false) {
         long long st;
         const float* a = frame_ptr(u, st) + st;
-        if (s == 0) bulk_copy2_g2s(xw, a, xw + Cfg::CH1, a + P.channel_stride, Cfg::N * 4, bar);
+        if (s == 0) {
+            if (last_chunk) bulk_copy2_g2s(xw + 768, a + 1536, xw + Cfg::CH1 + 768, a + P.channel_stride + 1536, 512 * 4, bar);
+            else bulk_copy2_g2s(xw, a, xw + Cfg::CH1, a + P.channel_stride, Cfg::N * 4, bar);
+        }
 #if defined(JADE_EMU)
         __syncwarp();
 #endif
     };
     // samples x window and the first butterfly stage of the 64-point DFT over n1 -> v (bit-reversed order); pair j = n1 j, j + 32.
     // c0 / st: channel-0 base and first sample index of the frame (PKZ_GUARD only).
-    auto load_pair = [&](f2* v, int j, const float* c0, long long st) {
-        const float4 wa4 = wrow[j / 4], wb4 = wrow[(j + 32) / 4];
-        const float wa = (j & 3) == 0 ? wa4.x : (j & 3) == 1 ? wa4.y : (j & 3) == 2 ? wa4.z : wa4.w;
-        const float wb = (j & 3) == 0 ? wb4.x : (j & 3) == 1 ? wb4.y : (j & 3) == 2 ? wb4.z : wb4.w;
-        if (LD == PKZ_ASYNC) {
+    auto load_pair = [&](f2* v, int j, const float* c0, long long st, float wa, float wb) {
+        if (STAGED) {
             win_stage1_64(v, j, pk(x0[32 * j], x1[32 * j]), wa, pk(x0[32 * (j + 32)], x1[32 * (j + 32)]), wb);
         } else {
             const float* c1 = c0 + P.channel_stride;
@@ -239,7 +335,20 @@ JADE_KERNEL(PkzCfg::WARPS * 32, 1) stft_pkz2048_kernel(const KParams P)
         }
     };
 
-    if (LD == PKZ_ASYNC && my_iters > 0) stage(cur);
+    if (STAGED && my_iters > 0) stage(cur);
+    // PKZ_RING: chunk c of the current frame sits in ring slot (ring + c) & 3, columns tring + 32 slot + 2 i + channel for n1 = 16 c + i
+    unsigned ring = 0;
+    const uint32_t tring = tq + 128u * (1u + ((unsigned)warp >> 2));
+    bool warm = false; // the current frame starts one chunk after the previous frame of this warp (three chunks in the ring already)
+    auto ingest = [&](int c) { // chunk c of the staged frame -> its ring slot
+        uint32_t xs[32];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            xs[2 * i] = f2u(x0[32 * (16 * c + i)]);
+            xs[2 * i + 1] = f2u(x1[32 * (16 * c + i)]);
+        }
+        tm_st<32>(tring + 32 * ((ring + c) & 3u), xs);
+    };
 
     // eps = 1e-11 (Spectrogram.cpp:36) rides on the power FMAs: every output is the sum of one "low" power (register 0..15 of
     // a row, seeded with eps) and one "high" power (16..31, unseeded); lane 0 pairs row 0 with itself, so its DC and Nyquist
@@ -250,17 +359,64 @@ JADE_KERNEL(PkzCfg::WARPS * 32, 1) stft_pkz2048_kernel(const KParams P)
         const ColOut o = col_out(P, (int)cur.stream, P.first_col + cur.col);
         // ---- samples x window, stage 1 (the frame was staged while the previous one was in pass 2)
         f2 v[64];
-        if (LD == PKZ_ASYNC) {
+        if (STAGED) {
             mbar_wait(bar, copies & 1u);
             ++copies;
         }
         {
             long long st;
             const float* c0 = frame_ptr(cur, st);
+            if constexpr (RING) {
+                if (!warm) {
+                    ring = 0;
+                    ingest(0);
+                    ingest(1);
+                    ingest(2);
+                }
+                ingest(3);
+                tm_wait_st();
+                // eight pairs at a time: samples n1 = 8 c .. + 7 (slot of chunk c >> 1) and 32 + 8 c .. + 7 (chunk (c >> 1) + 2), window chunk c
+                uint32_t xa[2][16], xb[2][16], wq[2][16];
+                auto fetch = [&](int c) {
+                    tm_ld<16>(tring + 32 * ((ring + (c >> 1)) & 3u) + 16 * (c & 1), xa[c & 1]);
+                    tm_ld<16>(tring + 32 * ((ring + (c >> 1) + 2) & 3u) + 16 * (c & 1), xb[c & 1]);
+                    tm_ld<16>(tq + 64 + 16 * c, wq[c & 1]);
+                };
+                fetch(0);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) load_pair(v, j, c0, st);
+                for (int c = 0; c < 4; ++c) {
+                    tm_wait_ld<16>(xa[c & 1]);
+                    tm_tie<16>(xb[c & 1]);
+                    tm_tie<16>(wq[c & 1]);
+                    if (c < 3) fetch(c + 1);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        win_stage1_64(v, 8 * c + i, pk(u2f(xa[c & 1][2 * i]), u2f(xa[c & 1][2 * i + 1])), u2f(wq[c & 1][i]),
+                                      pk(u2f(xb[c & 1][2 * i]), u2f(xb[c & 1][2 * i + 1])), u2f(wq[c & 1][8 + i]));
+                }
+                ring = (ring + 1) & 3u;
+            } else if constexpr (Cfg::TM) {
+                // window chunk c (n1 = 8 c .. + 7 and 32 + 8 c .. + 7) comes back from tensor memory while chunk c - 1 is consumed
+                uint32_t wq[2][16];
+                tm_ld<16>(tq + 64, wq[0]);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    tm_wait_ld<16>(wq[c & 1]);
+                    if (c < 3) tm_ld<16>(tq + 64 + 16 * (c + 1), wq[(c + 1) & 1]);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) load_pair(v, 8 * c + i, c0, st, u2f(wq[c & 1][i]), u2f(wq[c & 1][8 + i]));
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float4 wa4 = wrow[j / 4], wb4 = wrow[(j + 32) / 4];
+                    const float wa = (j & 3) == 0 ? wa4.x : (j & 3) == 1 ? wa4.y : (j & 3) == 2 ? wa4.z : wa4.w;
+                    const float wb = (j & 3) == 0 ? wb4.x : (j & 3) == 1 ? wb4.y : (j & 3) == 2 ? wb4.z : wb4.w;
+                    load_pair(v, j, c0, st, wa, wb);
+                }
+            }
         }
-        if (LD == PKZ_ASYNC) __syncwarp(); // every lane has read its samples before the transpose overwrites them
+        if (STAGED) __syncwarp(); // every lane has read its samples before the transpose overwrites them
         fft64_pk_after_stage1(v); // v[k1] = Y[s, k1]
 #pragma unroll
         for (int k1 = 0; k1 < 64; ++k1) xw[k1 * Cfg::XROW + s] = v[k1];
@@ -278,10 +434,33 @@ JADE_KERNEL(PkzCfg::WARPS * 32, 1) stft_pkz2048_kernel(const KParams P)
         const bool more = it + 1 < my_iters;
         if (more) {
             nxt.next();
-            if (LD == PKZ_ASYNC) stage(nxt);
+            if constexpr (RING) {
+                // the next frame continues this one (same stream, one chunk further): three of its chunks are in the ring already
+                warm = nxt.col != 0 && frame_start(P, P.first_col + nxt.col) == frame_start(P, P.first_col + cur.col) + Cfg::N / 4;
+                stage(nxt, warm);
+            } else if (STAGED) {
+                stage(nxt);
+            }
         }
-        fft32_twisted(ua, trowa); // ua[k2] = Z[s  + 64 k2]
-        fft32_twisted(ub, trowb); // ub[k2] = Z[kb + 64 k2]
+        if constexpr (Cfg::TM) {
+            // twisted tables from tensor memory, eight entries (16 columns) at a time, the next eight in flight behind them
+            uint32_t ta[16], tb[16];
+            tm_ld<16>(tq, ta);
+            tm_wait_ld<16>(ta);
+            tm_ld<16>(tq + 16, tb);
+            fft32_twisted_lo(ua, ta); // ua[k2] = Z[s  + 64 k2]
+            tm_wait_ld<16>(tb);
+            tm_ld<16>(tq + 32, ta);
+            fft32_twisted_hi(ua, tb);
+            tm_wait_ld<16>(ta);
+            tm_ld<16>(tq + 48, tb);
+            fft32_twisted_lo(ub, ta); // ub[k2] = Z[kb + 64 k2]
+            tm_wait_ld<16>(tb);
+            fft32_twisted_hi(ub, tb);
+        } else {
+            fft32_twisted(ua, trowa); // ua[k2] = Z[s  + 64 k2]
+            fft32_twisted(ub, trowb); // ub[k2] = Z[kb + 64 k2]
+        }
         // mean power of bin k (+ eps): |Z[k]|^2 + |Z[N-k]|^2.  Row s: bins s + 64 k2 mirror into row 64 - s at 31 - k2 (lane 0: row 0
         // at 32 - k2); row kb likewise into row s (lane 0: row 32 into itself).
         // (the packed form -- (re_a^2 + re_b^2 + eps, im_a^2 + im_b^2) by two FFMA2, then one FADD -- issues one instruction
@@ -315,6 +494,11 @@ JADE_KERNEL(PkzCfg::WARPS * 32, 1) stft_pkz2048_kernel(const KParams P)
             if (s == 0) pkz_emit<WANT_DB>(omid, (!WANT_DB || o.pix) ? o.pix : nullptr, (WANT_DB && o.db) ? o.db + 1024 : nullptr, P, s_pal);
         }
         cur = nxt;
+    }
+    if constexpr (Cfg::TM) {
+        tm_fence_before_sync();
+        __syncthreads();
+        if (threadIdx.x < 32) tm_dealloc(tq, Cfg::TM_COLS); // warp 0: quadrant 0 = the allocation's base address
     }
 }
 

@@ -24,6 +24,7 @@ struct BlockState {
     pthread_barrier_t block_bar;
     std::vector<pthread_barrier_t> warp_bar;
     std::vector<char> smem;
+    std::vector<uint32_t> tmem = std::vector<uint32_t>(128 * 512, 0u); // tensor memory: [lane][column] words (jade_tmem.cuh)
     std::vector<float> mail; // one slot per thread: warp shuffles
     std::vector<unsigned long long> mail64;
     // named barriers (PTX bar.sync / bar.arrive id, count): arrivals counted per id, a generation per completed barrier
@@ -37,6 +38,7 @@ inline dim3 g_blockDim, g_gridDim;
 // the block a thread belongs to (thread-local: the two CTAs of a cluster run at the same time, launch_cluster)
 inline thread_local BlockState* g_block = nullptr;
 inline void* dyn_smem() { return g_block->smem.data(); }
+inline uint32_t* tmem() { return g_block->tmem.data(); }
 // thread-block cluster of two CTAs: rank of this CTA, the peer's state, one barrier over all threads of the cluster
 struct ClusterState {
     BlockState* cta[2] = {nullptr, nullptr};

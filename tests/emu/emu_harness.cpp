@@ -57,6 +57,7 @@ void run_pk_one(const KParams& P, int npal, int grid)
         if (pair_ok && !pair2) {
             const int zs = jade::PkzCfg::smem_bytes(npal), zb = jade::PkzCfg::WARPS * 32;
             if (GUARD || !P.aligned4) jade_emu::launch(jade::stft_pkz2048_kernel<true, jade::PKZ_GUARD>, grid, zb, zs, P);
+            else if (getenv("JADE_EMU_RING")) jade_emu::launch(jade::stft_pkz2048_kernel<WDB, jade::PKZ_RING>, grid, zb, zs, P); // launch_one: long evenly spaced runs
             else jade_emu::launch(jade::stft_pkz2048_kernel<WDB, jade::PKZ_ASYNC>, grid, zb, zs, P);
         }
         else if (GUARD) jade_emu::launch(jade::stft_pk2048_kernel<MIXK, WDB, jade::PK_LD_GUARD>, grid, block, jade::PkCfg::smem_bytes(npal), P);

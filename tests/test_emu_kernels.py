@@ -73,7 +73,7 @@ def test_emulated_pkz2048_complex_stereo(monkeypatch, window, want_db):
     (stft_pkz2048_kernel, |X_L|^2 + |X_R|^2 = (|Z[k]|^2 + |Z[N-k]|^2) / 2).  Against the oracle over a chain of frames per
     warp (TMA staging of the next frame, rotated loop), and the TMA-staged instantiation bit-identical to the guarded one
     (streaming == batch == sharded relies on it)."""
-    for k in ("JADE_EMU_NOPAIR", "JADE_EMU_PAIR2", "JADE_EMU_FORCE_GUARD"):
+    for k in ("JADE_EMU_NOPAIR", "JADE_EMU_PAIR2", "JADE_EMU_FORCE_GUARD", "JADE_EMU_RING"):
         monkeypatch.delenv(k, raising=False)
     N, hop, ncols = 2048, 512, 53
     x = signals.streams(2, 2, hop * (ncols - 1) + 64, 48000.0, kind="mix")
@@ -90,6 +90,14 @@ def test_emulated_pkz2048_complex_stereo(monkeypatch, window, want_db):
     assert np.array_equal(gpix, pix)
     if want_db:
         assert np.array_equal(gdb, db)
+    # the long-run instantiation (contiguous columns per warp, samples in a tensor-memory ring of four chunks): runs that start
+    # in the middle of a stream and cross into the next one
+    monkeypatch.delenv("JADE_EMU_FORCE_GUARD")
+    monkeypatch.setenv("JADE_EMU_RING", "1")
+    rdb, rpix = E.render(_cfg(N, hop, 2, window, "absmean"), pal, -50.0, 50.0, x, 0, ncols, N // 2 + 1, grid=1, want_db=want_db)
+    assert np.array_equal(rpix, pix)
+    if want_db:
+        assert np.array_equal(rdb, db)
 
 
 _PAIR_RESULTS = {}
