@@ -26,6 +26,7 @@
 #include "jade_pk_cta.cuh"
 #include "jade_pk_small.cuh"
 #include "jade_pkz.cuh"
+#include "jade_pk3.cuh"
 #include "jade_pk_cluster.cuh"
 
 using jade::KParams;
@@ -64,6 +65,7 @@ kernel_fn pk2048_kernel(int mixk, bool want_db, int load);        // jade_k_pk.c
 kernel_fn pk2048x2_kernel(bool want_db);                           // jade_k_pk2.cu (stereo: two real transforms per warp; experiments)
 kernel_fn pkz2048_kernel(bool want_db, bool guard);                // jade_k_pkz.cu (stereo: one complex transform per frame)
 kernel_fn pkz2048_run_kernel(bool want_db);
+kernel_fn pk3_kernel(bool want_db, bool guard);                    // jade_k_pk3.cu (N = 16384, one contributing channel: three register passes)
 kernel_fn pksmall_kernel(int T, int mixk, bool want_db, bool guard); // jade_k_pksmall_a.cu / _b.cu
 } // namespace jade_k
 namespace {
@@ -366,6 +368,25 @@ int choose_kernel(jade_engine* e)
         default: return fail(e, JADE_ERR_ARG, "unsupported fft_size %d", N);
         }
         if (!kc.fn) return fail(e, JADE_ERR_ARG, "unsupported fft_size %d", N);
+    } else if (N == 16384 && !po && mu == jade::MIX_NONE && jade::Pk3Cfg::smem_bytes(e->npal) <= e->smem_optin / 2 &&
+               !(getenv("JADE_N16384") && !strcmp(getenv("JADE_N16384"), "cta"))) { // (the environment switch: experiments)
+        // one contributing channel: the three-pass kernel (jade_pk3.cuh); launch_stft routes interior, 16-byte aligned frames
+        // to the TMA-staged instantiation and the rest to the guarded one, like the packed N <= 2048 kernels
+        kc.family = 3;
+        kc.threads = jade::Pk3Cfg::THREADS;
+        kc.units_per_block = 1;
+        kc.smem = jade::Pk3Cfg::smem_bytes(e->npal);
+        snprintf(kc.name, sizeof kc.name, "pk3<16384>");
+        KernelChoice ke = kc;
+        snprintf(ke.name, sizeof ke.name, "pk3<16384>-guard");
+        kc.fn = jade_k::pk3_kernel(false, false);
+        kc.fn_db = jade_k::pk3_kernel(true, false);
+        ke.fn = jade_k::pk3_kernel(true, true);
+        ke.fn_db = nullptr;
+        CU(e, cudaFuncSetAttribute((const void*)kc.fn_db, cudaFuncAttributeMaxDynamicSharedMemorySize, kc.smem));
+        CU(e, cudaFuncSetAttribute((const void*)ke.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, ke.smem));
+        ke.blocks_per_sm = 2; // (see the note on the occupancy query below)
+        e->kc_edge = ke;
     } else if (N <= 32768) {
         const int R1 = N / 2048;
         kc.family = 1;
@@ -414,6 +435,10 @@ int choose_kernel(jade_engine* e)
     CU(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)kc.fn, kc.threads, kc.smem));
     if (occ < 1) return fail(e, JADE_ERR_CUDA, "kernel %s does not fit on an SM (smem %d)", kc.name, kc.smem);
     kc.blocks_per_sm = occ;
+    // (the occupancy query answers 1 for any kernel that contains tcgen05.alloc, whatever it allocates; the three-pass kernel
+    // takes 256 of the 512 tensor-memory columns and two of its CTAs do share an SM -- launch__waves_per_multiprocessor in
+    // profiles/r02c_pk3_16384.txt)
+    if (kc.family == 3 && N == 16384) kc.blocks_per_sm = 2;
     if (kc.family == 4) {
         // how many clusters fit at once (GPCs with an odd number of SMs leave one unpaired): the persistent grid is exactly that
         cudaLaunchConfig_t lc = {};
@@ -521,6 +546,8 @@ int launch_one(jade_engine* e, const KernelChoice& kc, KParams& P, cudaStream_t 
             return fail(e, JADE_ERR_STATE, "scratch not sized for grid %d", grid);
     }
     void* args[] = {(void*)&P};
+    static const bool trace = getenv("JADE_TRACE_LAUNCH") != nullptr; // experiments: one line per launch on stderr
+    if (trace) fprintf(stderr, "[jade] %s grid %d x %d threads, smem %d, blocks/SM %d, frames %lld\n", kc.name, grid, kc.threads, kc.smem, kc.blocks_per_sm, frames);
     kernel_fn fn = (P.db && kc.fn_db) ? kc.fn_db : kc.fn;
     // long runs of evenly spaced columns, a quarter frame apart: the instantiation that walks contiguous columns per warp
     static const bool no_run = [] { const char* v = getenv("JADE_PK_LOAD"); return v && !strcmp(v, "norun"); }(); // experiments

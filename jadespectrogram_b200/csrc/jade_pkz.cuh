@@ -106,18 +106,6 @@ JADE_HD int twz_exponent(int k1, int t)
 JADE_HD int pkz_row_b(int l) { return l == 0 ? 32 : 64 - l; }
 
 // the twisted pass in two halves with the table held in registers (raw words of f2 entries t = 0..7, then 8..15)
-JADE_DEVICE float u2f(uint32_t u)
-{
-    float f;
-    memcpy(&f, &u, 4);
-    return f;
-}
-JADE_DEVICE uint32_t f2u(float f)
-{
-    uint32_t u;
-    memcpy(&u, &f, 4);
-    return u;
-}
 JADE_DEVICE void fft32_twisted_lo(f2* u, const uint32_t* r)
 {
     f2 w[8];

@@ -13,6 +13,8 @@
 #include <stdint.h>
 #include <string.h>
 
+#include "jade_fft_regs.cuh"
+
 namespace jade {
 
 #if defined(JADE_EMU)
@@ -159,5 +161,19 @@ __device__ __forceinline__ void tm_wait_ld<32>(uint32_t* r)
                    "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])JADE_TM_CLOB);
 }
 #endif
+
+// raw words <-> floats (tensor-memory traffic is in 32-bit words)
+JADE_HD float u2f(uint32_t u)
+{
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+JADE_HD uint32_t f2u(float f)
+{
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    return u;
+}
 
 } // namespace jade

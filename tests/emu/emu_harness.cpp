@@ -8,6 +8,7 @@
 #include "../../jadespectrogram_b200/csrc/jade_pk_cta.cuh"
 #include "../../jadespectrogram_b200/csrc/jade_pk_small.cuh"
 #include "../../jadespectrogram_b200/csrc/jade_pkz.cuh"
+#include "../../jadespectrogram_b200/csrc/jade_pk3.cuh"
 #include "../../jadespectrogram_b200/csrc/jade_pk_cluster.cuh"
 #include "../../jadespectrogram_b200/csrc/jade_host_tables.h"
 #include "../../include/jade_gpu.h"
@@ -238,6 +239,30 @@ extern "C" int emu_render(const jade_config* cin, const int32_t* palette, int np
             if (multi == jade::MIX_SEL) jade_emu::launch(jade::stft_pkcta2_kernel<16, jade::MIX_SEL>, grid, 512, smem, P);
             else if (multi == jade::MIX_SUM) jade_emu::launch(jade::stft_pkcta2_kernel<16, jade::MIX_SUM>, grid, 512, smem, P);
             else jade_emu::launch(jade::stft_pkcta2_kernel<16, jade::MIX_NONE>, grid, 512, smem, P);
+        } else if (N == 16384 && !general && multi == jade::MIX_NONE && !getenv("JADE_EMU_PKCTA")) {
+            // the product route (choose_kernel / launch_stft): three-pass kernel, TMA-staged for interior 16-byte aligned frames,
+            // guarded for the rest
+            auto start = [&](long long j) {
+                return (j / c.frames_per_block) * (long long)c.block_stride + (j % c.frames_per_block) * (long long)c.hop - c.preroll;
+            };
+            const long long j0 = first_col, j1 = first_col + ncols;
+            long long lo = j0, hi = j1;
+            while (lo < j1 && start(lo) < 0) ++lo;
+            while (hi > lo && start(hi - 1) + N > nsamples) --hi;
+            if (!P.aligned4 || getenv("JADE_EMU_FORCE_GUARD")) lo = hi = j0;
+            const int smem = jade::Pk3Cfg::smem_bytes(npal);
+            for (int part = 0; part < 3; ++part) {
+                const long long a = part == 0 ? lo : (part == 1 ? j0 : hi), b = part == 0 ? hi : (part == 1 ? lo : j1);
+                if (b <= a) continue;
+                KParams Q = P;
+                Q.first_col = a;
+                Q.ncols = (int)(b - a);
+                if (Q.pix) Q.pix += (a - j0) * R;
+                if (Q.db) Q.db += (a - j0) * B;
+                if (part != 0) jade_emu::launch(jade::stft_pk3_kernel<true, jade::PK3_GUARD>, grid, 256, smem, Q);
+                else if (db) jade_emu::launch(jade::stft_pk3_kernel<true, jade::PK3_STAGED>, grid, 256, smem, Q);
+                else jade_emu::launch(jade::stft_pk3_kernel<false, jade::PK3_STAGED>, grid, 256, smem, Q);
+            }
         } else if (!general && multi != jade::MIX_SEL) {
             switch (R1) {
             case 2: run_pkcta<2>(P, multi, db != nullptr, npal, grid); break;

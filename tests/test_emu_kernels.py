@@ -100,6 +100,31 @@ def test_emulated_pkz2048_complex_stereo(monkeypatch, window, want_db):
         assert np.array_equal(rdb, db)
 
 
+@pytest.mark.parametrize("want_db", [True, False])
+def test_emulated_pk3_16384(monkeypatch, want_db):
+    """N = 16384, one contributing channel -- the product route: three register passes 32 x 16 x 16 by one CTA, tables in
+    tensor memory, split from registers (stft_pk3_kernel).  Interior frames through the TMA-staged instantiation (a chain of
+    frames per CTA: the next frame is staged while the current one is in pass 3), boundary frames through the guarded one;
+    against the oracle, and staged == guarded bit for bit (streaming == batch == sharded relies on it)."""
+    for k in ("JADE_EMU_FORCE_GUARD", "JADE_EMU_PKCTA"):
+        monkeypatch.delenv(k, raising=False)
+    N, hop, ncols = 16384, 4096, 9
+    x = signals.streams(2, 2, hop * (ncols - 1) - 4096, 96000.0, kind="mix")  # the last columns run past the end
+    pal = O.Palette(256, O.PAL["jade"]).table()
+    cfg = _cfg(N, hop, 2, "blackmanharris", "right")
+    db, pix = E.render(cfg, pal, -50.0, 50.0, x, 0, ncols, N // 2 + 1, grid=2, want_db=want_db)
+    for s in range(x.shape[0]):
+        odb, opix = O.render_batch(x[s], fft_size=N, hop=hop, window="blackmanharris", mix="right", ncols=ncols)
+        if want_db:
+            parity.check_db(db[s], odb, N, f"stream {s}")
+        parity.check_pixels(pix[s], opix, odb[:, ::-1], -50.0, 50.0, 256, f"stream {s}")
+    monkeypatch.setenv("JADE_EMU_FORCE_GUARD", "1")
+    gdb, gpix = E.render(cfg, pal, -50.0, 50.0, x, 0, ncols, N // 2 + 1, grid=3, want_db=True)
+    assert np.array_equal(gpix, pix)
+    if want_db:
+        assert np.array_equal(gdb, db)
+
+
 _PAIR_RESULTS = {}
 
 

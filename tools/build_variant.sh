@@ -14,6 +14,6 @@ if [ -n "$3" ]; then $NV -c jade_k_pkcta.cu -o $out/obj_$name/jade_k_pkcta.o 2> 
 wait
 PKCTA=jade_k_pkcta.o; [ -n "$3" ] && PKCTA=$out/obj_$name/jade_k_pkcta.o
 nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $out/lib_$name.so $out/obj_$name/jade_gpu.o $out/obj_$name/jade_k_pk.o $out/obj_$name/jade_k_pk2.o $out/obj_$name/jade_k_pkz.o \
-  jade_k_pksmall_a.o jade_k_pksmall_b.o $PKCTA jade_k_pkcl.o jade_k_warp_a.o jade_k_warp_b.o jade_k_cta.o jade_host_tables.o jade_view.o jade_axis.o
+  jade_k_pksmall_a.o jade_k_pksmall_b.o $PKCTA jade_k_pk3.o jade_k_pkcl.o jade_k_warp_a.o jade_k_warp_b.o jade_k_cta.o jade_host_tables.o jade_view.o jade_axis.o
 grep -A2 "pkz2048_kernelILb0ELi0" $out/obj_$name/pkz.ptxas.log | grep -E "registers|spill" | paste - - | sed 's/ptxas info    ://g' | cut -c1-200
 grep -A2 "pk2048_kernelILi1ELb0ELi0\|pk2048_kernelILi0ELb0ELi0\|pk2048_kernelILi1ELb0ELi1" $out/obj_$name/pk.ptxas.log | grep -E "registers|spill" | paste - - | sed 's/ptxas info    ://g' | cut -c1-200
