@@ -27,6 +27,7 @@
 #include "jade_pk_small.cuh"
 #include "jade_pkz.cuh"
 #include "jade_pk3.cuh"
+#include "jade_pk_cluster3.cuh"
 #include "jade_pk_cluster.cuh"
 
 using jade::KParams;
@@ -60,6 +61,7 @@ kernel_fn warp_kernel(int T, int mixk, bool general);             // jade_k_warp
 kernel_fn cta_kernel(int R1, int mixk, bool general);             // jade_k_cta.cu
 kernel_fn pkcta_kernel(int R1, int mixk, bool want_db);           // jade_k_pkcta.cu
 kernel_fn pkcta2_kernel(int mixk);                                // jade_k_pkcta.cu (N = 65536 on one CTA; experiments)
+kernel_fn pkcl3_kernel();                                         // jade_k_pkcl.cu (N = 65536, one contributing channel)
 kernel_fn pkcl65536_kernel(int mixk);                             // jade_k_pkcl.cu (N = 65536 on a cluster of two CTAs)
 kernel_fn pk2048_kernel(int mixk, bool want_db, int load);        // jade_k_pk.cu (load = jade::PK_LD_*)
 kernel_fn pk2048x2_kernel(bool want_db);                           // jade_k_pk2.cu (stereo: two real transforms per warp; experiments)
@@ -420,9 +422,17 @@ int choose_kernel(jade_engine* e)
         } else {
             // one frame per cluster of two CTAs: the two half-size transforms run on two SMs and meet through DSMEM
             kc.family = 4;
-            snprintf(kc.name, sizeof kc.name, "pkcl65536");
-            kc.fn = jade_k::pkcl65536_kernel(mu);
-            kc.smem = jade::PkClCfg::smem_bytes(e->npal, e->pooled ? e->R : 0);
+            static const bool old_cl = [] { const char* v = getenv("JADE_N65536"); return v && !strcmp(v, "cl"); }(); // experiments
+            const int smem3 = jade::PkCl3Cfg::smem_bytes(e->npal, e->pooled ? e->R : 0);
+            if (mu == jade::MIX_NONE && !old_cl && smem3 <= e->smem_optin) {
+                snprintf(kc.name, sizeof kc.name, "pkcl3<65536>");
+                kc.fn = jade_k::pkcl3_kernel();
+                kc.smem = smem3;
+            } else {
+                snprintf(kc.name, sizeof kc.name, "pkcl65536");
+                kc.fn = jade_k::pkcl65536_kernel(mu);
+                kc.smem = jade::PkClCfg::smem_bytes(e->npal, e->pooled ? e->R : 0);
+            }
         }
     } else {
         return fail(e, JADE_ERR_ARG, "unsupported fft_size %d (power of two in [64,65536])", N);

@@ -9,6 +9,7 @@
 #include "../../jadespectrogram_b200/csrc/jade_pk_small.cuh"
 #include "../../jadespectrogram_b200/csrc/jade_pkz.cuh"
 #include "../../jadespectrogram_b200/csrc/jade_pk3.cuh"
+#include "../../jadespectrogram_b200/csrc/jade_pk_cluster3.cuh"
 #include "../../jadespectrogram_b200/csrc/jade_pk_cluster.cuh"
 #include "../../jadespectrogram_b200/csrc/jade_host_tables.h"
 #include "../../include/jade_gpu.h"
@@ -230,6 +231,10 @@ extern "C" int emu_render(const jade_config* cin, const int32_t* palette, int np
             if (!getenv("JADE_EMU_CTA2")) { // the product route: a cluster of two CTAs per frame (jade_pk_cluster.cuh)
                 const int smem = jade::PkClCfg::smem_bytes(npal, pooled ? R : 0);
                 const unsigned cg = 2u * (unsigned)((grid + 1) / 2);
+                if (multi == jade::MIX_NONE && !getenv("JADE_EMU_PKCL")) { // one contributing channel: jade_pk_cluster3.cuh
+                    jade_emu::launch_cluster2(jade::stft_pkcl3_kernel<jade::MIX_NONE>, cg, 512, jade::PkCl3Cfg::smem_bytes(npal, pooled ? R : 0), P);
+                    return R;
+                }
                 if (multi == jade::MIX_SEL) jade_emu::launch_cluster2(jade::stft_pkcl65536_kernel<jade::MIX_SEL>, cg, 512, smem, P);
                 else if (multi == jade::MIX_SUM) jade_emu::launch_cluster2(jade::stft_pkcl65536_kernel<jade::MIX_SUM>, cg, 512, smem, P);
                 else jade_emu::launch_cluster2(jade::stft_pkcl65536_kernel<jade::MIX_NONE>, cg, 512, smem, P);

@@ -11,7 +11,7 @@ ROOT = pathlib.Path(__file__).resolve().parent.parent
 EMU_DIR = ROOT / "tests" / "emu"
 SO = EMU_DIR / "libjade_emu.so"
 SRCS = [EMU_DIR / "emu_harness.cpp", EMU_DIR / "cuda_emu.h", ROOT / "jadespectrogram_b200/csrc/jade_kernels.cuh",
-        ROOT / "jadespectrogram_b200/csrc/jade_fft_regs.cuh", ROOT / "jadespectrogram_b200/csrc/jade_pk.cuh", ROOT / "jadespectrogram_b200/csrc/jade_pkz.cuh", ROOT / "jadespectrogram_b200/csrc/jade_tmem.cuh", ROOT / "jadespectrogram_b200/csrc/jade_pk3.cuh", ROOT / "jadespectrogram_b200/csrc/jade_pk_cluster.cuh", ROOT / "jadespectrogram_b200/csrc/jade_pk_cta.cuh", ROOT / "jadespectrogram_b200/csrc/jade_pk_small.cuh", ROOT / "jadespectrogram_b200/csrc/jade_host_tables.cpp"]
+        ROOT / "jadespectrogram_b200/csrc/jade_fft_regs.cuh", ROOT / "jadespectrogram_b200/csrc/jade_pk.cuh", ROOT / "jadespectrogram_b200/csrc/jade_pkz.cuh", ROOT / "jadespectrogram_b200/csrc/jade_tmem.cuh", ROOT / "jadespectrogram_b200/csrc/jade_pk3.cuh", ROOT / "jadespectrogram_b200/csrc/jade_pk_cluster3.cuh", ROOT / "jadespectrogram_b200/csrc/jade_pk_cluster.cuh", ROOT / "jadespectrogram_b200/csrc/jade_pk_cta.cuh", ROOT / "jadespectrogram_b200/csrc/jade_pk_small.cuh", ROOT / "jadespectrogram_b200/csrc/jade_host_tables.cpp"]
 
 
 def build():

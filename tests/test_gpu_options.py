@@ -56,7 +56,7 @@ def test_cfg5_geometry_log_rows_n65536(gpu_engine_factory):
     fs, N, hop, R = 192000.0, 65536, 1024, 1080
     x = signals.streams(1, 1, N + hop * 8, fs)
     eng = gpu_engine_factory(sample_rate=fs, fft_size=N, hop=hop, channels=1, row_map="log_maxpool", rows=R, fmin=20.0, fmax=96000.0)
-    assert eng.kernel_name == "pkcl65536"
+    assert eng.kernel_name == "pkcl3<65536>"  # one contributing channel: three register passes per CTA (jade_pk_cluster3.cuh)
     pix, db = eng.render_batch(x, first_col=64, ncols=6, want_db=True)
     odb, _ = O.render_batch(x[0], fs=fs, fft_size=N, hop=hop, first_col=64, ncols=6)
     parity.check_db(db[0], odb, N)
