@@ -19,6 +19,13 @@
 // Same reference lines replaced as jade_kernels.cuh (Spectrogram.cpp:50-56,137-145,64-107,634-647; CColorpalette.h:32-47).
 #pragma once
 #include "jade_pk.cuh"
+#include "jade_tmem.cuh"
+
+// JADE_PKS_TMEM = 1: the per-lane window, twisted-twiddle and split-twiddle tables (128 words per lane) live in tensor memory
+// (jade_tmem.cuh) instead of shared memory: a quarter of the kernel's shared-memory wavefronts
+#ifndef JADE_PKS_TMEM
+#define JADE_PKS_TMEM 1
+#endif
 
 // occupancy: T >= 8 (N = 512, 1024): 12 warps per SM with up to 168 registers (one CTA); smaller T: 16 warps of 128
 // registers (two CTAs of 8) -- measured both ways for every T (gpurun_out: 12 x 1 is +6 % at N = 1024, -7 % at N = 128).
@@ -84,12 +91,14 @@ struct PkSmallCfg {
     // per-frame tile (f2 words): 32 rows of T+1 for the transpose (and the landing area of the next frame); the stride
     // between the F tiles of a warp is kept == T (mod 16) so that frames sharing a half-warp hit disjoint banks
     static constexpr int FS = 32 * (T + 1) + (T < 16 ? T : 0);
+    static constexpr bool TM = JADE_PKS_TMEM != 0 && T >= 8; // (N = 128 / 256, two CTAs per SM: 3 % slower with it, gpurun_out/pks1.txt)
+    static constexpr int TM_COLS = 128; // tensor-memory columns per lane: window 0..63 (in the order pass 1 consumes it), twisted table 64..95, split table 96..127
     static constexpr int off_win = 0;
-    static constexpr int off_twI = off_win + T * ROW * 8;
-    static constexpr int off_twP = off_twI + T * ROW * 8;
-    static constexpr int off_pal = off_twP + T * PROW * 8;
-    static JADE_HD int off_bar(int npal) { return off_pal + (npal * 4 + 15) / 16 * 16; } // one mbarrier per warp
-    static JADE_HD int off_xch(int npal) { return off_bar(npal) + (WARPS * 8 + 15) / 16 * 16; }
+    static constexpr int off_twI = off_win + (TM ? 0 : T * ROW * 8);
+    static constexpr int off_twP = off_twI + (TM ? 0 : T * ROW * 8);
+    static constexpr int off_pal = off_twP + (TM ? 0 : T * PROW * 8);
+    static JADE_HD int off_bar(int npal) { return off_pal + (npal * 4 + 15) / 16 * 16; } // one mbarrier per warp (+ the tensor-memory address)
+    static JADE_HD int off_xch(int npal) { return off_bar(npal) + (WARPS * 8 + 8 + 15) / 16 * 16; }
     static JADE_HD int smem_bytes(int npal) { return off_xch(npal) + WARPS * F * FS * 8; }
 };
 
@@ -118,6 +127,55 @@ JADE_KERNEL(PkSmallCfg<T>::WARPS * 32, PkSmallCfg<T>::CTAS) stft_pksmall_kernel(
     f2* s_xch = reinterpret_cast<f2*>(sm + Cfg::off_xch(P.npal));
 
     if (!GUARD && threadIdx.x < Cfg::WARPS) mbar_init(s_bar + threadIdx.x, 1);
+    uint32_t tq = 0; // tensor-memory address of this warp's quadrant of the tables
+    if constexpr (Cfg::TM) {
+        uint32_t* s_tm = reinterpret_cast<uint32_t*>(s_bar + Cfg::WARPS);
+        if (threadIdx.x < 32) tm_alloc(s_tm, Cfg::TM_COLS);
+        tm_fence_before_sync();
+        __syncthreads();
+        tm_fence_after_sync();
+        tq = tm_quadrant_base(*s_tm);
+        if (threadIdx.x < 128) { // warp q fills quadrant q: the tables of lane l depend on s = l % T only
+            const int s = (threadIdx.x & 31) % T;
+            uint32_t r[16];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { // window chunk c: points n1 = 4c .. 4c+3, then 16 + 4c .. 16 + 4c + 3 (m = s + T n1)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int ma = s + T * (4 * c + i), mb = ma + 16 * T;
+                    r[2 * i] = f2u(P.window[2 * ma]);
+                    r[2 * i + 1] = f2u(P.window[2 * ma + 1]);
+                    r[8 + 2 * i] = f2u(P.window[2 * mb]);
+                    r[8 + 2 * i + 1] = f2u(P.window[2 * mb + 1]);
+                }
+                tm_st<16>(tq + 16 * c, r);
+            }
+#pragma unroll
+            for (int c = 0; c < 2; ++c) { // twisted pass-2 table: entry q = ip (T/2) + t for row k1 = s + T ip
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int q = 8 * c + i, ip = q / H, t = q % H;
+                    const cpx w = P.twP[2 * twr_exponent<T>(s + T * ip, t)]; // W_M^e = W_N^{2e}
+                    r[2 * i] = f2u(w.x);
+                    r[2 * i + 1] = f2u(w.y);
+                }
+                tm_st<16>(tq + 64 + 16 * c, r);
+            }
+#pragma unroll
+            for (int c = 0; c < 2; ++c) { // split table: pair q = ip H + k2: k = s + T ip + 32 k2, entry -i W_N^k = (w.y, -w.x)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int q = 8 * c + i;
+                    const cpx w = P.twP[s + T * (q / H) + 32 * (q % H)];
+                    r[2 * i] = f2u(w.y);
+                    r[2 * i + 1] = f2u(-w.x);
+                }
+                tm_st<16>(tq + 96 + 16 * c, r);
+            }
+            tm_wait_st();
+        }
+        tm_fence_before_sync();
+    } else {
     // ---- per-s tables: entry (s, index) at [s*ROW + index]
     for (int i = threadIdx.x; i < M; i += blockDim.x) {
         const int s = i % T, n1 = i / T;                         // m = s + T n1
@@ -133,8 +191,10 @@ JADE_KERNEL(PkSmallCfg<T>::WARPS * 32, PkSmallCfg<T>::CTAS) stft_pksmall_kernel(
         const cpx w = P.twP[s + T * (q / H) + 32 * (q % H)];     // W_N^k ; table holds -i W_N^k = (w.y, -w.x)
         s_twP[s * Cfg::PROW + q] = pk(w.y, -w.x);
     }
+    }
     for (int i = threadIdx.x; i < P.npal; i += blockDim.x) s_pal[i] = P.palette[i];
     __syncthreads();
+    if constexpr (Cfg::TM) tm_fence_after_sync();
     grid_dep_wait();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -202,9 +262,26 @@ JADE_KERNEL(PkSmallCfg<T>::WARPS * 32, PkSmallCfg<T>::CTAS) stft_pksmall_kernel(
                 mbar_wait(bar, copies & 1u);
                 ++copies;
             }
+            uint32_t wq[2][16]; // window chunks from tensor memory, one ahead
+            if constexpr (Cfg::TM) tm_ld<16>(tq, wq[0]);
 #pragma unroll
             for (int jj = 0; jj < 16; jj += 2) { // n1 = jj, jj+1 paired with n1 + 16
-                const f2x2 wa = wrow[jj / 2], wb = wrow[(jj + 16) / 2];
+                f2x2 wa, wb;
+                if constexpr (Cfg::TM) {
+                    const int c = jj / 4, o = 4 * ((jj / 2) & 1);
+                    if ((jj & 2) == 0) {
+                        tm_wait_ld<16>(wq[c & 1]);
+                        if (c < 3) tm_ld<16>(tq + 16 * (c + 1), wq[(c + 1) & 1]);
+                    }
+                    const uint32_t* w = wq[c & 1];
+                    wa.a = pk(u2f(w[o]), u2f(w[o + 1]));
+                    wa.b = pk(u2f(w[o + 2]), u2f(w[o + 3]));
+                    wb.a = pk(u2f(w[8 + o]), u2f(w[8 + o + 1]));
+                    wb.b = pk(u2f(w[8 + o + 2]), u2f(w[8 + o + 3]));
+                } else {
+                    wa = wrow[jj / 2];
+                    wb = wrow[(jj + 16) / 2];
+                }
                 f2 xa0, xa1, xb0, xb1;
                 if (!GUARD) {
                     const f2* xz = xw + s; // staged frame: z[m] at word m of the lane's tile
@@ -231,11 +308,19 @@ JADE_KERNEL(PkSmallCfg<T>::WARPS * 32, PkSmallCfg<T>::CTAS) stft_pksmall_kernel(
             for (int k1 = 0; k1 < 32; ++k1) tr_wr[k1 * TS] = v[k1];
             __syncwarp();
             f2 u[32], twl[16]; // this lane's 16 twisted twiddles: T/2 per row
+            if constexpr (Cfg::TM) {
+                uint32_t tw[32];
+                tm_ld<32>(tq + 64, tw);
+                tm_wait_ld<32>(tw);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const f2x2 t = trow[i];
-                twl[2 * i] = t.a;
-                twl[2 * i + 1] = t.b;
+                for (int i = 0; i < 16; ++i) twl[i] = pk(u2f(tw[2 * i]), u2f(tw[2 * i + 1]));
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const f2x2 t = trow[i];
+                    twl[2 * i] = t.a;
+                    twl[2 * i + 1] = t.b;
+                }
             }
 #pragma unroll
             for (int i = 0; i < F; ++i) {
@@ -250,15 +335,28 @@ JADE_KERNEL(PkSmallCfg<T>::WARPS * 32, PkSmallCfg<T>::CTAS) stft_pksmall_kernel(
             }
             // Pair split.  Z[M - k] of pair q = i H + k2 (k = s + T i + 32 k2) is register (F-1-i) T + (T-1-k2) of lane
             // T - s of the same frame and arrives by SHFL.IDX; lane s = 0 pairs with its own lane0_partner<T>(q).
+            uint32_t pw[16]; // split table from tensor memory: pairs 0..7, then 8..15
 #pragma unroll
             for (int q = 0; q < 16; ++q) {
+                if constexpr (Cfg::TM) {
+                    if ((q & 7) == 0) {
+                        tm_ld<16>(tq + 96 + 2 * q, pw);
+                        tm_wait_ld<16>(pw);
+                    }
+                }
                 const int iq = q / H, k2 = q % H;
                 const int uq = iq * T + k2;
                 const f2 zp = sel2(s == 0, u[lane0_partner<T>(q)], shfl2(u[(F - 1 - iq) * T + (T - 1 - k2)], plane));
-                const f2x2 wq = prow[q / 2];
+                f2 wsp;
+                if constexpr (Cfg::TM) {
+                    wsp = pk(u2f(pw[2 * (q & 7)]), u2f(pw[2 * (q & 7) + 1]));
+                } else {
+                    const f2x2 wq2 = prow[q / 2];
+                    wsp = (q & 1) ? wq2.b : wq2.a;
+                }
                 const f2 A = add2(u[uq], conj2(zp));  // Z[k] + conj Z[M-k]
                 const f2 Bv = sub2(u[uq], conj2(zp)); // Z[k] - conj Z[M-k]
-                const f2 Tw = cmul2(Bv, (q & 1) ? wq.b : wq.a);
+                const f2 Tw = cmul2(Bv, wsp);
                 const f2 xp = add2(A, Tw), xm = sub2(A, Tw);
                 alo[q] = fm(lo(xp), lo(xp), fm(hi(xp), hi(xp), alo[q]));
                 ahi[q] = fm(lo(xm), lo(xm), fm(hi(xm), hi(xm), ahi[q]));
@@ -283,6 +381,11 @@ JADE_KERNEL(PkSmallCfg<T>::WARPS * 32, PkSmallCfg<T>::CTAS) stft_pksmall_kernel(
             emit_bin<MIXK, WANT_DB>(ahi[q], scale, (!WANT_DB || p_hi) ? p_hi + koff : nullptr, d_hi ? d_hi - koff : nullptr, P, s_pal);
         }
         if (s == 0) emit_bin<MIXK, WANT_DB>(amid, scale, (!WANT_DB || o.pix) ? o.pix + M / 2 : nullptr, (WANT_DB && o.db) ? o.db + M / 2 : nullptr, P, s_pal);
+    }
+    if constexpr (Cfg::TM) {
+        tm_fence_before_sync();
+        __syncthreads();
+        if (threadIdx.x < 32) tm_dealloc(tq, Cfg::TM_COLS); // warp 0: quadrant 0 = the allocation's base address
     }
 }
 

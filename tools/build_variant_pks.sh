@@ -10,5 +10,5 @@ $NV -c jade_k_pksmall_b.cu -o $out/obj_$name/jade_k_pksmall_b.o 2> $out/obj_$nam
 $NV -c jade_gpu.cu -o $out/obj_$name/jade_gpu.o 2> $out/obj_$name/gpu.ptxas.log &
 wait
 nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $out/lib_$name.so $out/obj_$name/jade_gpu.o jade_k_pk.o jade_k_pk2.o \
-  $out/obj_$name/jade_k_pksmall_a.o $out/obj_$name/jade_k_pksmall_b.o jade_k_pkcta.o jade_k_warp_a.o jade_k_warp_b.o jade_k_cta.o jade_host_tables.o jade_view.o
+  $out/obj_$name/jade_k_pksmall_a.o $out/obj_$name/jade_k_pksmall_b.o jade_k_pkz.o jade_k_pkcta.o jade_k_pk3.o jade_k_pkcl.o jade_k_warp_a.o jade_k_warp_b.o jade_k_cta.o jade_host_tables.o jade_view.o jade_axis.o
 grep -A2 "stft_pksmall_kernelILi16ELi0ELb0ELb0" $out/obj_$name/pksb.ptxas.log | grep -E "registers|spill" | paste - - | sed 's/ptxas info    ://g' | cut -c1-200
