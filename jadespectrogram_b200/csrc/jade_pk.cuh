@@ -27,6 +27,7 @@
 // in registers, one transpose through shared memory, twisted radix-32 in registers: lane s ends with Z[s + 32 k2].
 #pragma once
 #include "jade_kernels.cuh"
+#include "jade_tmem.cuh"
 
 namespace jade {
 
@@ -421,6 +422,30 @@ JADE_DEVICE void fft32_twisted2(f2* ua, f2* ub, const f2x2* trow)
     tw32_half2<4>(ua, ub, JADE_TROW(6), JADE_TROW(7));
 }
 
+// the twisted pass in two halves with the table held in registers (raw words of f2 entries t = 0..7, then 8..15)
+JADE_DEVICE void fft32_twisted_lo(f2* u, const uint32_t* r)
+{
+    f2 w[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) w[i] = pk(u2f(r[2 * i]), u2f(r[2 * i + 1]));
+    tw_blocks<2, 0>(u, w);
+    tw_blocks<4, 0>(u, w + 1);
+    tw_blocks<8, 0>(u, w + 2);
+    tw_blocks<16, 0>(u, w + 4);
+}
+JADE_DEVICE void fft32_twisted_hi(f2* u, const uint32_t* r)
+{
+    f2x2 t[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        t[i].a = pk(u2f(r[4 * i]), u2f(r[4 * i + 1]));
+        t[i].b = pk(u2f(r[4 * i + 2]), u2f(r[4 * i + 3]));
+    }
+    tw32_half<0>(u, t[0], t[1]);
+    tw32_half<4>(u, t[2], t[3]);
+}
+
+
 // ---------------------------------------------------------------------------------------------------------
 // occupancy: JADE_PK_WARPS warps per CTA, JADE_PK_CTAS CTAs per SM (register cap = 65536 / (32 WARPS CTAS))
 #ifndef JADE_PK_WARPS
@@ -437,12 +462,19 @@ struct PkCfg {
     static constexpr int PROW = 18;  // f2 words per lane row of the split-twiddle table (16 + 16 B pad)
     static constexpr int XROW = 34;  // f2 words per transpose row: 16-byte aligned rows, conflict-free LDS.128
     static constexpr int XCH = 32 * XROW; // f2 words per warp buffer: transpose, and landing area of the next frame (1024)
+#ifndef JADE_PK_TMEM
+#define JADE_PK_TMEM 1
+#endif
+    // per-lane window / twisted / split tables in tensor memory (jade_tmem.cuh) instead of shared memory; one CTA per SM only
+    // (the engine's occupancy query answers 1 for kernels with tcgen05.alloc)
+    static constexpr bool TM = JADE_PK_TMEM != 0 && JADE_PK_CTAS == 1;
+    static constexpr int TM_COLS = 128; // window 0..63 (in the order pass 1 consumes it), twisted table 64..95, split table 96..127
     static constexpr int off_win = 0;
-    static constexpr int off_tw2 = off_win + 32 * ROW * 8;
-    static constexpr int off_twP = off_tw2 + 32 * TROW * 8;
-    static constexpr int off_pal = off_twP + 32 * PROW * 8;
-    static JADE_HD int off_bar(int npal) { return off_pal + (npal * 4 + 15) / 16 * 16; } // one mbarrier per warp
-    static JADE_HD int off_xch(int npal) { return off_bar(npal) + (WARPS * 8 + 15) / 16 * 16; }
+    static constexpr int off_tw2 = off_win + (TM ? 0 : 32 * ROW * 8);
+    static constexpr int off_twP = off_tw2 + (TM ? 0 : 32 * TROW * 8);
+    static constexpr int off_pal = off_twP + (TM ? 0 : 32 * PROW * 8);
+    static JADE_HD int off_bar(int npal) { return off_pal + (npal * 4 + 15) / 16 * 16; } // one mbarrier per warp (+ the tensor-memory address)
+    static JADE_HD int off_xch(int npal) { return off_bar(npal) + (WARPS * 8 + 8 + 15) / 16 * 16; }
     static JADE_HD int smem_bytes(int npal) { return off_xch(npal) + WARPS * XCH * 8; }
 };
 
@@ -518,21 +550,70 @@ JADE_KERNEL(PkCfg::WARPS * 32, JADE_PK_CTAS) stft_pk2048_kernel(const KParams P)
     unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(sm + Cfg::off_bar(P.npal));
     f2* s_xch = reinterpret_cast<f2*>(sm + Cfg::off_xch(P.npal));
 
-    // ---- per-lane tables: entry for (lane s, index i) at [s*ROW + i]
-    for (int i = threadIdx.x; i < M; i += blockDim.x) {
-        const int s = i & 31, n1 = i >> 5;                       // m = s + 32 n1
-        s_win[s * Cfg::ROW + n1] = pk(P.window[2 * i], P.window[2 * i + 1]);
-    }
     if (LD == PK_LD_ASYNC && threadIdx.x < Cfg::WARPS) mbar_init(s_bar + threadIdx.x, 1);
-    for (int i = threadIdx.x; i < 512; i += blockDim.x) {
-        const int s = i & 31, q = i >> 5;
-        const cpx t = P.twP[2 * tw2_exponent(s, q)];             // W_1024^e = W_2048^{2e}
-        s_tw2[s * Cfg::TROW + q] = pk(t.x, t.y);
-        const cpx w = P.twP[s + 32 * q];                         // k = s + 32 q: table holds -i W_N^k = (w.y, -w.x)
-        s_twP[s * Cfg::PROW + q] = pk(w.y, -w.x);
+    uint32_t tq = 0; // tensor-memory address of this warp's quadrant of the tables
+    if constexpr (Cfg::TM) {
+        uint32_t* s_tm = reinterpret_cast<uint32_t*>(s_bar + Cfg::WARPS);
+        if (threadIdx.x < 32) tm_alloc(s_tm, Cfg::TM_COLS);
+        tm_fence_before_sync();
+        __syncthreads();
+        tm_fence_after_sync();
+        tq = tm_quadrant_base(*s_tm);
+        if (threadIdx.x < 128) { // warp q fills quadrant q: thread l writes the tables of lane l
+            const int l = threadIdx.x & 31;
+            uint32_t r[16];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { // window chunk c: points n1 = 4c .. 4c+3, then 16 + 4c .. 16 + 4c + 3 (m = l + 32 n1)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int ma = l + 32 * (4 * c + i), mb = ma + 512;
+                    r[2 * i] = f2u(P.window[2 * ma]);
+                    r[2 * i + 1] = f2u(P.window[2 * ma + 1]);
+                    r[8 + 2 * i] = f2u(P.window[2 * mb]);
+                    r[8 + 2 * i + 1] = f2u(P.window[2 * mb + 1]);
+                }
+                tm_st<16>(tq + 16 * c, r);
+            }
+#pragma unroll
+            for (int c = 0; c < 2; ++c) { // twisted pass-2 table
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const cpx w = P.twP[2 * tw2_exponent(l, 8 * c + i)]; // W_1024^e = W_2048^{2e}
+                    r[2 * i] = f2u(w.x);
+                    r[2 * i + 1] = f2u(w.y);
+                }
+                tm_st<16>(tq + 64 + 16 * c, r);
+            }
+#pragma unroll
+            for (int c = 0; c < 2; ++c) { // split table: k = l + 32 q, entry -i W_N^k = (w.y, -w.x)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const cpx w = P.twP[l + 32 * (8 * c + i)];
+                    r[2 * i] = f2u(w.y);
+                    r[2 * i + 1] = f2u(-w.x);
+                }
+                tm_st<16>(tq + 96 + 16 * c, r);
+            }
+            tm_wait_st();
+        }
+        tm_fence_before_sync();
+    } else {
+        // ---- per-lane tables: entry for (lane s, index i) at [s*ROW + i]
+        for (int i = threadIdx.x; i < M; i += blockDim.x) {
+            const int s = i & 31, n1 = i >> 5;                       // m = s + 32 n1
+            s_win[s * Cfg::ROW + n1] = pk(P.window[2 * i], P.window[2 * i + 1]);
+        }
+        for (int i = threadIdx.x; i < 512; i += blockDim.x) {
+            const int s = i & 31, q = i >> 5;
+            const cpx t = P.twP[2 * tw2_exponent(s, q)];             // W_1024^e = W_2048^{2e}
+            s_tw2[s * Cfg::TROW + q] = pk(t.x, t.y);
+            const cpx w = P.twP[s + 32 * q];                         // k = s + 32 q: table holds -i W_N^k = (w.y, -w.x)
+            s_twP[s * Cfg::PROW + q] = pk(w.y, -w.x);
+        }
     }
     for (int i = threadIdx.x; i < P.npal; i += blockDim.x) s_pal[i] = P.palette[i];
     __syncthreads();
+    if constexpr (Cfg::TM) tm_fence_after_sync();
     grid_dep_wait();
 
     const int s = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -578,9 +659,26 @@ JADE_KERNEL(PkCfg::WARPS * 32, JADE_PK_CTAS) stft_pk2048_kernel(const KParams P)
                 pk_prefetch_wait(bar, copies & 1u);
                 ++copies;
             }
+            uint32_t wq[2][16]; // window chunks from tensor memory, one ahead
+            if constexpr (Cfg::TM) tm_ld<16>(tq, wq[0]);
 #pragma unroll
             for (int jj = 0; jj < 16; jj += 2) { // n1 = jj, jj+1 paired with n1 + 16
-                const f2x2 wa = wrow[jj / 2], wb = wrow[(jj + 16) / 2];
+                f2x2 wa, wb;
+                if constexpr (Cfg::TM) {
+                    const int c = jj / 4, o = 4 * ((jj / 2) & 1);
+                    if ((jj & 2) == 0) {
+                        tm_wait_ld<16>(wq[c & 1]);
+                        if (c < 3) tm_ld<16>(tq + 16 * (c + 1), wq[(c + 1) & 1]);
+                    }
+                    const uint32_t* w = wq[c & 1];
+                    wa.a = pk(u2f(w[o]), u2f(w[o + 1]));
+                    wa.b = pk(u2f(w[o + 2]), u2f(w[o + 3]));
+                    wb.a = pk(u2f(w[8 + o]), u2f(w[8 + o + 1]));
+                    wb.b = pk(u2f(w[8 + o + 2]), u2f(w[8 + o + 3]));
+                } else {
+                    wa = wrow[jj / 2];
+                    wb = wrow[(jj + 16) / 2];
+                }
                 f2 xa0, xa1, xb0, xb1;
                 if (LD == PK_LD_ASYNC) {
                     const f2* xz = xw + s;
@@ -631,17 +729,40 @@ JADE_KERNEL(PkCfg::WARPS * 32, JADE_PK_CTAS) stft_pk2048_kernel(const KParams P)
                     pk_prefetch(xw, P.samples + nx.stream * P.stream_stride + ch0 * P.channel_stride + nx.st, s, bar);
                 }
             }
-            fft32_twisted(u, trow); // u[k2] = Z[s + 32 k2]
+            if constexpr (Cfg::TM) { // twisted table from tensor memory, eight entries at a time
+                uint32_t ta[16], tb[16];
+                tm_ld<16>(tq + 64, ta);
+                tm_wait_ld<16>(ta);
+                tm_ld<16>(tq + 80, tb);
+                fft32_twisted_lo(u, ta);
+                tm_wait_ld<16>(tb);
+                fft32_twisted_hi(u, tb);
+            } else {
+                fft32_twisted(u, trow); // u[k2] = Z[s + 32 k2]
+            }
+            // split table: pairs 0..7, then 8..15 (tensor memory) / two entries per LDS.128 (shared memory)
+            uint32_t pw[16];
+            auto split_tw = [&](int q) {
+                if constexpr (Cfg::TM) {
+                    if ((q & 7) == 0) {
+                        tm_ld<16>(tq + 96 + 2 * q, pw);
+                        tm_wait_ld<16>(pw);
+                    }
+                    return pk(u2f(pw[2 * (q & 7)]), u2f(pw[2 * (q & 7) + 1]));
+                } else {
+                    const f2x2 wq2 = prow[q / 2];
+                    return (q & 1) ? wq2.b : wq2.a;
+                }
+            };
             // Real-FFT split per pair (k, M-k), k = s + 32 q.  Z[M-k] is register 31 - q of lane 32 - s; lane 0 pairs with
             // its own register 32 - q.  The last channel goes straight on to dB / colour / store.
             if (!last) {
 #pragma unroll
                 for (int q = 0; q < 16; ++q) {
                     const f2 zp = sel2(s == 0, u[(32 - q) & 31], shfl2(u[31 - q], partner));
-                    const f2x2 wq = prow[q / 2];
                     const f2 A = add2(u[q], conj2(zp));  // Z[k] + conj Z[M-k]
                     const f2 Bv = sub2(u[q], conj2(zp)); // Z[k] - conj Z[M-k]
-                    const f2 T = cmul2(Bv, (q & 1) ? wq.b : wq.a);
+                    const f2 T = cmul2(Bv, split_tw(q));
                     const f2 xp = add2(A, T), xm = sub2(A, T);
                     alo[q] = fm(lo(xp), lo(xp), fm(hi(xp), hi(xp), alo[q]));
                     ahi[q] = fm(lo(xm), lo(xm), fm(hi(xm), hi(xm), ahi[q]));
@@ -656,10 +777,9 @@ JADE_KERNEL(PkCfg::WARPS * 32, JADE_PK_CTAS) stft_pk2048_kernel(const KParams P)
 #pragma unroll
                 for (int q = 0; q < 16; ++q) {
                     const f2 zp = sel2(s == 0, u[(32 - q) & 31], shfl2(u[31 - q], partner));
-                    const f2x2 wq = prow[q / 2];
                     const f2 A = add2(u[q], conj2(zp));
                     const f2 Bv = sub2(u[q], conj2(zp));
-                    const f2 T = cmul2(Bv, (q & 1) ? wq.b : wq.a);
+                    const f2 T = cmul2(Bv, split_tw(q));
                     const f2 xp = add2(A, T), xm = sub2(A, T);
                     const float pl = fm(lo(xp), lo(xp), fm(hi(xp), hi(xp), MIXK == MIX_NONE ? 0.f : alo[q]));
                     const float ph = fm(lo(xm), lo(xm), fm(hi(xm), hi(xm), MIXK == MIX_NONE ? 0.f : ahi[q]));
@@ -673,6 +793,11 @@ JADE_KERNEL(PkCfg::WARPS * 32, JADE_PK_CTAS) stft_pk2048_kernel(const KParams P)
                 }
             }
         }
+    }
+    if constexpr (Cfg::TM) {
+        tm_fence_before_sync();
+        __syncthreads();
+        if (threadIdx.x < 32) tm_dealloc(tq, Cfg::TM_COLS); // warp 0: quadrant 0 = the allocation's base address
     }
 }
 
@@ -693,7 +818,12 @@ JADE_KERNEL(PkCfg::WARPS * 32, JADE_PK_CTAS) stft_pk2048_kernel(const KParams P)
 // ---------------------------------------------------------------------------------------------------------
 struct PkPairCfg {
     static constexpr int WARPS = 12;
-    static JADE_HD int off_bar(int npal) { return PkCfg::off_pal + (npal * 4 + 15) / 16 * 16; }
+    // (its own shared-memory tables: PkCfg's moved to tensor memory)
+    static constexpr int off_win = 0;
+    static constexpr int off_tw2 = off_win + 32 * PkCfg::ROW * 8;
+    static constexpr int off_twP = off_tw2 + 32 * PkCfg::TROW * 8;
+    static constexpr int off_pal = off_twP + 32 * PkCfg::PROW * 8;
+    static JADE_HD int off_bar(int npal) { return off_pal + (npal * 4 + 15) / 16 * 16; }
     static JADE_HD int off_xch(int npal) { return off_bar(npal) + (WARPS * 8 + 15) / 16 * 16; }
     static JADE_HD int smem_bytes(int npal) { return off_xch(npal) + WARPS * 2 * PkCfg::XCH * 8; }
 };
@@ -705,10 +835,10 @@ JADE_KERNEL(PkPairCfg::WARPS * 32, 1) stft_pk2048x2_kernel(const KParams P)
     constexpr int M = Cfg::M, WARPS = PkPairCfg::WARPS, XCH = Cfg::XCH;
     JADE_DYN_SMEM(smem);
     char* sm = reinterpret_cast<char*>(smem);
-    f2* s_win = reinterpret_cast<f2*>(sm + Cfg::off_win);
-    f2* s_tw2 = reinterpret_cast<f2*>(sm + Cfg::off_tw2);
-    f2* s_twP = reinterpret_cast<f2*>(sm + Cfg::off_twP);
-    uint32_t* s_pal = reinterpret_cast<uint32_t*>(sm + Cfg::off_pal);
+    f2* s_win = reinterpret_cast<f2*>(sm + PkPairCfg::off_win);
+    f2* s_tw2 = reinterpret_cast<f2*>(sm + PkPairCfg::off_tw2);
+    f2* s_twP = reinterpret_cast<f2*>(sm + PkPairCfg::off_twP);
+    uint32_t* s_pal = reinterpret_cast<uint32_t*>(sm + PkPairCfg::off_pal);
     unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(sm + PkPairCfg::off_bar(P.npal));
     f2* s_xch = reinterpret_cast<f2*>(sm + PkPairCfg::off_xch(P.npal));
 

@@ -105,29 +105,6 @@ JADE_HD int twz_exponent(int k1, int t)
 // second row of lane l
 JADE_HD int pkz_row_b(int l) { return l == 0 ? 32 : 64 - l; }
 
-// the twisted pass in two halves with the table held in registers (raw words of f2 entries t = 0..7, then 8..15)
-JADE_DEVICE void fft32_twisted_lo(f2* u, const uint32_t* r)
-{
-    f2 w[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) w[i] = pk(u2f(r[2 * i]), u2f(r[2 * i + 1]));
-    tw_blocks<2, 0>(u, w);
-    tw_blocks<4, 0>(u, w + 1);
-    tw_blocks<8, 0>(u, w + 2);
-    tw_blocks<16, 0>(u, w + 4);
-}
-JADE_DEVICE void fft32_twisted_hi(f2* u, const uint32_t* r)
-{
-    f2x2 t[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        t[i].a = pk(u2f(r[4 * i]), u2f(r[4 * i + 1]));
-        t[i].b = pk(u2f(r[4 * i + 2]), u2f(r[4 * i + 3]));
-    }
-    tw32_half<0>(u, t[0], t[1]);
-    tw32_half<4>(u, t[2], t[3]);
-}
-
 struct PkzCfg {
     static constexpr int N = 2048, B = 1025;
 #ifndef JADE_PKZ_WARPS
