@@ -41,7 +41,8 @@ typedef void (*kernel_fn)(const KParams);
 struct KernelChoice {
     kernel_fn fn = nullptr;
     kernel_fn fn_db = nullptr; // variant that also stores the float dB column (only where the two differ)
-    kernel_fn fn_run = nullptr, fn_run_db = nullptr; // variant for long runs of evenly spaced columns with hop = N/4 (pkz2048: PKZ_RING)
+    kernel_fn fn_run = nullptr, fn_run_db = nullptr; // variant for long runs of evenly spaced columns run_hop samples apart (tensor-memory sample ring)
+    int run_hop = 0;
     int threads = 0;
     int smem = 0;
     int blocks_per_sm = 1;
@@ -67,6 +68,7 @@ kernel_fn pk2048_kernel(int mixk, bool want_db, int load);        // jade_k_pk.c
 kernel_fn pk2048x2_kernel(bool want_db);                           // jade_k_pk2.cu (stereo: two real transforms per warp; experiments)
 kernel_fn pkz2048_kernel(bool want_db, bool guard);                // jade_k_pkz.cu (stereo: one complex transform per frame)
 kernel_fn pkz2048_run_kernel(bool want_db);
+kernel_fn pk2048_run_kernel(bool want_db, int hop);                // jade_k_pk2.cu (one channel, hop 256 / 512: tensor-memory sample ring)
 kernel_fn pk3_kernel(bool want_db, bool guard);                    // jade_k_pk3.cu (N = 16384, one contributing channel: three register passes)
 kernel_fn pksmall_kernel(int T, int mixk, bool want_db, bool guard); // jade_k_pksmall_a.cu / _b.cu
 } // namespace jade_k
@@ -287,6 +289,13 @@ int choose_kernel(jade_engine* e)
         snprintf(ke.name, sizeof ke.name, "%s-guard", kc.name);
         kc.fn = T == 32 ? jade_k::pk2048_kernel(mu, false, jade::PK_LD_ASYNC) : jade_k::pksmall_kernel(T, mu, false, false);
         kc.fn_db = T == 32 ? jade_k::pk2048_kernel(mu, true, jade::PK_LD_ASYNC) : jade_k::pksmall_kernel(T, mu, true, false);
+        if (T == 32 && mu == jade::MIX_NONE && jade::PkCfg::TM && jade_k::pk2048_run_kernel(false, e->cfg.hop)) {
+            kc.fn_run = jade_k::pk2048_run_kernel(false, e->cfg.hop);
+            kc.fn_run_db = jade_k::pk2048_run_kernel(true, e->cfg.hop);
+            kc.run_hop = e->cfg.hop;
+            CU(e, cudaFuncSetAttribute((const void*)kc.fn_run, cudaFuncAttributeMaxDynamicSharedMemorySize, kc.smem));
+            CU(e, cudaFuncSetAttribute((const void*)kc.fn_run_db, cudaFuncAttributeMaxDynamicSharedMemorySize, kc.smem));
+        }
         ke.fn = T == 32 ? jade_k::pk2048_kernel(mu, true, jade::PK_LD_GUARD) : jade_k::pksmall_kernel(T, mu, true, true);
         if (!kc.fn || !kc.fn_db || !ke.fn) return fail(e, JADE_ERR_ARG, "unsupported fft_size %d", N);
         if (T == 32) {
@@ -327,6 +336,7 @@ int choose_kernel(jade_engine* e)
                     ke = kp;
                     kp.fn_run = jade_k::pkz2048_run_kernel(false);
                     kp.fn_run_db = jade_k::pkz2048_run_kernel(true);
+                    kp.run_hop = 512;
                     snprintf(ke.name, sizeof ke.name, "pkz2048-guard");
                     ke.fn = jade_k::pkz2048_kernel(true, true);
                     e->has_mid = false; // 8- but not 16-byte aligned frames: the guarded instantiation
@@ -561,7 +571,7 @@ int launch_one(jade_engine* e, const KernelChoice& kc, KParams& P, cudaStream_t 
     kernel_fn fn = (P.db && kc.fn_db) ? kc.fn_db : kc.fn;
     // long runs of evenly spaced columns, a quarter frame apart: the instantiation that walks contiguous columns per warp
     static const bool no_run = [] { const char* v = getenv("JADE_PK_LOAD"); return v && !strcmp(v, "norun"); }(); // experiments
-    if (kc.fn_run && !no_run && P.hop * 4 == P.N && (P.fb == 1 ? P.bstride == P.hop : P.bstride == P.fb * P.hop) &&
+    if (kc.fn_run && !no_run && P.hop == kc.run_hop && (P.fb == 1 ? P.bstride == P.hop : P.bstride == P.fb * P.hop) &&
         frames >= 16ll * grid * kc.units_per_block)
         fn = P.db ? kc.fn_run_db : kc.fn_run;
     if (P.ring_w > 0) {

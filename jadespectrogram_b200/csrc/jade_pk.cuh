@@ -468,7 +468,8 @@ struct PkCfg {
     // per-lane window / twisted / split tables in tensor memory (jade_tmem.cuh) instead of shared memory; one CTA per SM only
     // (the engine's occupancy query answers 1 for kernels with tcgen05.alloc)
     static constexpr bool TM = JADE_PK_TMEM != 0 && JADE_PK_CTAS == 1;
-    static constexpr int TM_COLS = 128; // window 0..63 (in the order pass 1 consumes it), twisted table 64..95, split table 96..127
+    static constexpr int TM_COLS = 512; // window 0..63 (in the order pass 1 consumes it), twisted table 64..95, split table 96..127; 128 + 64 (warp / 4) ..:
+                                        // that warp's sample ring (PK_LD_RING*; the warps w, w + 4, w + 8 share the lanes of quadrant w % 4)
     static constexpr int off_win = 0;
     static constexpr int off_tw2 = off_win + (TM ? 0 : 32 * ROW * 8);
     static constexpr int off_twP = off_tw2 + (TM ? 0 : 32 * TROW * 8);
@@ -489,7 +490,12 @@ struct PkCfg {
 //                  geometries; routed by launch_stft in jade_gpu.cu.
 // The arithmetic after the load is the same code in all three, so streaming, batch and sharded renderings of a column
 // agree bit for bit whichever instantiation produced it.
-enum { PK_LD_ASYNC = 0, PK_LD_DIRECT = 1, PK_LD_GUARD = 2 };
+//   PK_LD_RING4 / PK_LD_RING8 : staged like PK_LD_ASYNC, for long runs of evenly spaced columns with hop = 256 / 512 and one
+//                  contributing channel: every warp takes a contiguous run of columns and keeps the frame's 32 complex
+//                  values per lane in a tensor-memory ring of 8 / 4 chunks, so that a frame whose start lies one hop after
+//                  its predecessor's reads only its NEW chunk from shared memory and the TMA engine stages 1 / 2 KB per frame
+//                  instead of 8 (cf. PKZ_RING in jade_pkz.cuh).
+enum { PK_LD_ASYNC = 0, PK_LD_DIRECT = 1, PK_LD_GUARD = 2, PK_LD_RING4 = 3, PK_LD_RING8 = 4 };
 
 struct PkUnit {
     int stream;
@@ -541,6 +547,9 @@ JADE_KERNEL(PkCfg::WARPS * 32, JADE_PK_CTAS) stft_pk2048_kernel(const KParams P)
 {
     using Cfg = PkCfg;
     constexpr int M = Cfg::M;
+    constexpr bool RING = LD == PK_LD_RING4 || LD == PK_LD_RING8, STAGED = LD == PK_LD_ASYNC || RING;
+    constexpr int CH = LD == PK_LD_RING8 ? 8 : 4, NCH = 32 / CH; // ring: NCH chunks of CH values n1 (hop = 64 CH samples)
+    static_assert(!RING || (Cfg::TM && MIXK == MIX_NONE && Cfg::WARPS <= 12), "the sample ring: tensor memory, one contributing channel");
     JADE_DYN_SMEM(smem);
     char* sm = reinterpret_cast<char*>(smem);
     f2* s_win = reinterpret_cast<f2*>(sm + Cfg::off_win);
@@ -550,7 +559,7 @@ JADE_KERNEL(PkCfg::WARPS * 32, JADE_PK_CTAS) stft_pk2048_kernel(const KParams P)
     unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(sm + Cfg::off_bar(P.npal));
     f2* s_xch = reinterpret_cast<f2*>(sm + Cfg::off_xch(P.npal));
 
-    if (LD == PK_LD_ASYNC && threadIdx.x < Cfg::WARPS) mbar_init(s_bar + threadIdx.x, 1);
+    if (STAGED && threadIdx.x < Cfg::WARPS) mbar_init(s_bar + threadIdx.x, 1);
     uint32_t tq = 0; // tensor-memory address of this warp's quadrant of the tables
     if constexpr (Cfg::TM) {
         uint32_t* s_tm = reinterpret_cast<uint32_t*>(s_bar + Cfg::WARPS);
@@ -638,12 +647,41 @@ JADE_KERNEL(PkCfg::WARPS * 32, JADE_PK_CTAS) stft_pk2048_kernel(const KParams P)
     // in row M - k, so lane s writes rows M-s-32q (bins s+32q) and rows s+32q (bins M-s-32q): both coalesced.
     auto emit = [&](float p, uint32_t* pix, float* db) { emit_bin<MIXK, WANT_DB>(p, scale, pix, db, P, s_pal); };
 
-    unsigned g = blockIdx.x * Cfg::WARPS + warp;
-    if (LD == PK_LD_ASYNC && g < total) {
+    // frames of this warp: dealt round-robin (g, g + gstep, ...), or -- PK_LD_RING* -- one contiguous run
+    unsigned g = blockIdx.x * Cfg::WARPS + warp, g_end = total, g_inc = gstep;
+    if (RING) {
+        const unsigned per = (total + gstep - 1) / gstep;
+        g = min(total, g * per);
+        g_end = min(total, g + per);
+        g_inc = 1;
+    }
+    // PK_LD_RING*: chunk c of the current frame (n1 = CH c .. CH c + CH - 1) sits in ring slot (ring + c) % NCH, columns
+    // tring + 2 CH slot + 2 i (+ 1) for n1 = CH c + i
+    unsigned ring = 0;
+    bool warm = false; // the current frame starts one hop after the previous frame of this warp: all chunks but the last are in the ring
+    const uint32_t tring = tq + 128u + 64u * ((unsigned)warp >> 2);
+    auto ingest = [&](int c) { // chunk c of the staged frame -> its ring slot
+        uint32_t xs[2 * CH];
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+            const f2 z = xw[s + 32 * (CH * c + i)];
+            xs[2 * i] = f2u(lo(z));
+            xs[2 * i + 1] = f2u(hi(z));
+        }
+        tm_st<2 * CH>(tring + 2 * CH * ((ring + c) % NCH), xs);
+    };
+    // the frame's last chunk only (its first sample at src): 256 CH bytes, in place at the end of the buffer
+    auto prefetch_last = [&](const float* src) {
+        if (s == 0) bulk_copy_g2s(xw + 32 * (32 - CH), src + 64 * (32 - CH), 256 * CH, bar);
+#if defined(JADE_EMU)
+        __syncwarp();
+#endif
+    };
+    if (STAGED && g < g_end) {
         const PkUnit un = pk_unit(P, g);
         pk_prefetch(xw, P.samples + un.stream * P.stream_stride + ch0 * P.channel_stride + un.st, s, bar);
     }
-    for (; g < total; g += gstep) {
+    for (; g < g_end; g += g_inc) {
         const PkUnit un = pk_unit(P, g);
         const ColOut o = col_out(P, un.stream, un.j);
         const float* x = P.samples + un.stream * P.stream_stride + ch0 * P.channel_stride + un.st; // frame, channel ch
@@ -655,11 +693,27 @@ JADE_KERNEL(PkCfg::WARPS * 32, JADE_PK_CTAS) stft_pk2048_kernel(const KParams P)
         for (int ch = ch0; ch < ch1; ++ch, x += P.channel_stride) {
             const bool last = (MIXK == MIX_NONE) || (ch + 1 == ch1);
             f2 v[32];
-            if (LD == PK_LD_ASYNC) {
+            if (STAGED) {
                 pk_prefetch_wait(bar, copies & 1u);
                 ++copies;
             }
+            if constexpr (RING) {
+                if (!warm) {
+                    ring = 0;
+#pragma unroll
+                    for (int c = 0; c < NCH - 1; ++c) ingest(c);
+                }
+                ingest(NCH - 1);
+                tm_wait_st();
+            }
             uint32_t wq[2][16]; // window chunks from tensor memory, one ahead
+            uint32_t xq[2][2][8]; // PK_LD_RING*: the samples of the same points from the ring
+            auto ring_fetch = [&](int c) { // points n1 = 4c .. 4c+3 and 16 + 4c .. 16 + 4c + 3
+                const int na = 4 * c, nb = 16 + 4 * c;
+                tm_ld<8>(tring + 2 * CH * ((ring + na / CH) % NCH) + 2 * (na % CH), xq[c & 1][0]);
+                tm_ld<8>(tring + 2 * CH * ((ring + nb / CH) % NCH) + 2 * (nb % CH), xq[c & 1][1]);
+            };
+            if constexpr (RING) ring_fetch(0);
             if constexpr (Cfg::TM) tm_ld<16>(tq, wq[0]);
 #pragma unroll
             for (int jj = 0; jj < 16; jj += 2) { // n1 = jj, jj+1 paired with n1 + 16
@@ -668,6 +722,11 @@ JADE_KERNEL(PkCfg::WARPS * 32, JADE_PK_CTAS) stft_pk2048_kernel(const KParams P)
                     const int c = jj / 4, o = 4 * ((jj / 2) & 1);
                     if ((jj & 2) == 0) {
                         tm_wait_ld<16>(wq[c & 1]);
+                        if constexpr (RING) {
+                            tm_tie<8>(xq[c & 1][0]);
+                            tm_tie<8>(xq[c & 1][1]);
+                            if (c < 3) ring_fetch(c + 1);
+                        }
                         if (c < 3) tm_ld<16>(tq + 16 * (c + 1), wq[(c + 1) & 1]);
                     }
                     const uint32_t* w = wq[c & 1];
@@ -680,7 +739,15 @@ JADE_KERNEL(PkCfg::WARPS * 32, JADE_PK_CTAS) stft_pk2048_kernel(const KParams P)
                     wb = wrow[(jj + 16) / 2];
                 }
                 f2 xa0, xa1, xb0, xb1;
-                if (LD == PK_LD_ASYNC) {
+                if (RING) {
+                    const int c = jj / 4, o = 4 * ((jj / 2) & 1);
+                    const uint32_t* qa = xq[c & 1][0];
+                    const uint32_t* qb = xq[c & 1][1];
+                    xa0 = pk(u2f(qa[o]), u2f(qa[o + 1]));
+                    xa1 = pk(u2f(qa[o + 2]), u2f(qa[o + 3]));
+                    xb0 = pk(u2f(qb[o]), u2f(qb[o + 1]));
+                    xb1 = pk(u2f(qb[o + 2]), u2f(qb[o + 3]));
+                } else if (LD == PK_LD_ASYNC) {
                     const f2* xz = xw + s;
                     xa0 = xz[32 * jj];
                     xa1 = xz[32 * (jj + 1)];
@@ -706,7 +773,8 @@ JADE_KERNEL(PkCfg::WARPS * 32, JADE_PK_CTAS) stft_pk2048_kernel(const KParams P)
                 win_stage1(v, jj, xa0, wa.a, xb0, wb.a);
                 win_stage1(v, jj + 1, xa1, wa.b, xb1, wb.b);
             }
-            if (LD == PK_LD_ASYNC) __syncwarp(); // every lane has read its samples before the transpose overwrites them
+            if (RING) ring = (ring + 1) % NCH;
+            if (STAGED) __syncwarp(); // every lane has read its samples before the transpose overwrites them
             fft32_pk_after_stage1(v);
 #pragma unroll
             for (int k1 = 0; k1 < 32; ++k1) tr_wr[k1 * Cfg::XROW] = v[k1];
@@ -719,14 +787,22 @@ JADE_KERNEL(PkCfg::WARPS * 32, JADE_PK_CTAS) stft_pk2048_kernel(const KParams P)
                 u[brev(jx + 1, 5)] = t.b;
             }
             __syncwarp(); // the buffer is free again
-            if (LD == PK_LD_ASYNC) {
+            if (STAGED) {
                 // start the copy of what this warp transforms next: the next channel of this frame, or the first
                 // channel of its next frame
                 if (!last) {
                     pk_prefetch(xw, x + P.channel_stride, s, bar);
-                } else if (g + gstep < total) {
-                    const PkUnit nx = pk_unit(P, g + gstep);
-                    pk_prefetch(xw, P.samples + nx.stream * P.stream_stride + ch0 * P.channel_stride + nx.st, s, bar);
+                } else if (g + g_inc < g_end) {
+                    const PkUnit nx = pk_unit(P, g + g_inc);
+                    const float* nsrc = P.samples + nx.stream * P.stream_stride + ch0 * P.channel_stride + nx.st;
+                    if (RING) {
+                        // the next frame continues this one (same stream, one hop further): only its last chunk is new
+                        warm = nx.stream == un.stream && nx.st == un.st + 64 * CH;
+                        if (warm) prefetch_last(nsrc);
+                        else pk_prefetch(xw, nsrc, s, bar);
+                    } else {
+                        pk_prefetch(xw, nsrc, s, bar);
+                    }
                 }
             }
             if constexpr (Cfg::TM) { // twisted table from tensor memory, eight entries at a time

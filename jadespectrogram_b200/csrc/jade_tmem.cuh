@@ -66,6 +66,13 @@ __device__ __forceinline__ void tm_fence_after_sync() { asm volatile("tcgen05.fe
 template <int N>
 __device__ __forceinline__ void tm_st(uint32_t taddr, const uint32_t* r);
 template <>
+__device__ __forceinline__ void tm_st<8>(uint32_t taddr, const uint32_t* r)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]),
+                 "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+template <>
 __device__ __forceinline__ void tm_st<16>(uint32_t taddr, const uint32_t* r)
 {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
@@ -146,6 +153,11 @@ __device__ __forceinline__ void tm_wait_ld<16>(uint32_t* r)
 // tie further registers of loads that the preceding tm_wait_ld has completed
 template <int N>
 __device__ __forceinline__ void tm_tie(uint32_t* r);
+template <>
+__device__ __forceinline__ void tm_tie<8>(uint32_t* r)
+{
+    asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]));
+}
 template <>
 __device__ __forceinline__ void tm_tie<16>(uint32_t* r)
 {

@@ -65,6 +65,10 @@ void run_pk_one(const KParams& P, int npal, int grid)
         else if (GUARD) jade_emu::launch(jade::stft_pk2048_kernel<MIXK, WDB, jade::PK_LD_GUARD>, grid, block, jade::PkCfg::smem_bytes(npal), P);
         else if (P.aligned4 && pair_ok)
             jade_emu::launch(jade::stft_pk2048x2_kernel<WDB>, grid, jade::PkPairCfg::WARPS * 32, jade::PkPairCfg::smem_bytes(npal), P);
+        else if (P.aligned4 && MIXK == jade::MIX_NONE && getenv("JADE_EMU_RING") && (P.hop == 256 || P.hop == 512)) { // launch_one: long evenly spaced runs
+            if (P.hop == 256) jade_emu::launch(jade::stft_pk2048_kernel<jade::MIX_NONE, WDB, jade::PK_LD_RING4>, grid, block, jade::PkCfg::smem_bytes(npal), P);
+            else jade_emu::launch(jade::stft_pk2048_kernel<jade::MIX_NONE, WDB, jade::PK_LD_RING8>, grid, block, jade::PkCfg::smem_bytes(npal), P);
+        }
         else if (P.aligned4) jade_emu::launch(jade::stft_pk2048_kernel<MIXK, WDB, jade::PK_LD_ASYNC>, grid, block, jade::PkCfg::smem_bytes(npal), P);
         else jade_emu::launch(jade::stft_pk2048_kernel<MIXK, WDB, jade::PK_LD_DIRECT>, grid, block, jade::PkCfg::smem_bytes(npal), P);
     }

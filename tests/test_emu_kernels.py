@@ -125,6 +125,28 @@ def test_emulated_pk3_16384(monkeypatch, want_db):
         assert np.array_equal(gdb, db)
 
 
+@pytest.mark.parametrize("hop", [256, 512])
+def test_emulated_pk2048_mono_ring(monkeypatch, hop):
+    """N = 2048, one contributing channel, hop 256 / 512: the long-run instantiations of stft_pk2048_kernel (PK_LD_RING4 / RING8:
+    contiguous columns per warp, the frame's values in a tensor-memory ring of 8 / 4 chunks, only the last chunk staged for a
+    frame that continues its predecessor) are bit-identical to the round-robin instantiation, over runs that start in the
+    middle of a stream and cross into the next one."""
+    for k in ("JADE_EMU_NOPAIR", "JADE_EMU_PAIR2", "JADE_EMU_FORCE_GUARD", "JADE_EMU_RING"):
+        monkeypatch.delenv(k, raising=False)
+    N, ncols = 2048, 61
+    x = signals.streams(2, 2, hop * (ncols - 1) + 64, 48000.0, kind="mix")
+    pal = O.Palette(256, O.PAL["jade"]).table()
+    cfg = _cfg(N, hop, 2, "hamming", "left")
+    db, pix = E.render(cfg, pal, -50.0, 50.0, x, 0, ncols, N // 2 + 1, grid=1)
+    for s in range(x.shape[0]):
+        odb, opix = O.render_batch(x[s], fft_size=N, hop=hop, window="hamming", mix="left", ncols=ncols)
+        parity.check_db(db[s], odb, N, f"stream {s}")
+        parity.check_pixels(pix[s], opix, odb[:, ::-1], -50.0, 50.0, 256, f"stream {s}")
+    monkeypatch.setenv("JADE_EMU_RING", "1")
+    rdb, rpix = E.render(cfg, pal, -50.0, 50.0, x, 0, ncols, N // 2 + 1, grid=1)
+    assert np.array_equal(rpix, pix) and np.array_equal(rdb, db)
+
+
 _PAIR_RESULTS = {}
 
 
