@@ -399,6 +399,12 @@ int choose_kernel(jade_engine* e)
         CU(e, cudaFuncSetAttribute((const void*)ke.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, ke.smem));
         ke.blocks_per_sm = 2; // (see the note on the occupancy query below)
         e->kc_edge = ke;
+        if (getenv("JADE_N16384") && !strcmp(getenv("JADE_N16384"), "mixed")) { // experiment: one launch, staged / guarded decided per frame
+            kc.family = 1;
+            kc.fn = jade_k::pk3_kernel(false, true);
+            kc.fn_db = jade_k::pk3_kernel(true, true);
+            CU(e, cudaFuncSetAttribute((const void*)kc.fn_db, cudaFuncAttributeMaxDynamicSharedMemorySize, kc.smem));
+        }
     } else if (N <= 32768) {
         const int R1 = N / 2048;
         kc.family = 1;
@@ -458,7 +464,7 @@ int choose_kernel(jade_engine* e)
     // (the occupancy query answers 1 for any kernel that contains tcgen05.alloc, whatever it allocates; the three-pass kernel
     // takes 256 of the 512 tensor-memory columns and two of its CTAs do share an SM -- launch__waves_per_multiprocessor in
     // profiles/r02c_pk3_16384.txt)
-    if (kc.family == 3 && N == 16384) kc.blocks_per_sm = 2;
+    if ((kc.family == 3 || kc.family == 1) && N == 16384 && kc.threads == jade::Pk3Cfg::THREADS && kc.smem == jade::Pk3Cfg::smem_bytes(e->npal)) kc.blocks_per_sm = 2;
     if (kc.family == 4) {
         // how many clusters fit at once (GPCs with an odd number of SMs leave one unpaired): the persistent grid is exactly that
         cudaLaunchConfig_t lc = {};
@@ -550,7 +556,8 @@ int grid_for(jade_engine* e, const KernelChoice& kc, long long frames)
 {
     if (kc.family == 4) return (int)(2 * std::max<long long>(1, std::min<long long>(frames, kc.max_clusters)));
     const long long blocks_needed = (frames + kc.units_per_block - 1) / kc.units_per_block;
-    const long long cap = (long long)e->sm_count * kc.blocks_per_sm;
+    static const long long max_grid = [] { const char* v = getenv("JADE_MAX_GRID"); return v ? atoll(v) : 0ll; }(); // experiments / sanitizer runs
+    const long long cap = max_grid > 0 ? max_grid : (long long)e->sm_count * kc.blocks_per_sm;
     return (int)std::max<long long>(1, std::min(blocks_needed, cap));
 }
 
@@ -567,13 +574,16 @@ int launch_one(jade_engine* e, const KernelChoice& kc, KParams& P, cudaStream_t 
     }
     void* args[] = {(void*)&P};
     static const bool trace = getenv("JADE_TRACE_LAUNCH") != nullptr; // experiments: one line per launch on stderr
-    if (trace) fprintf(stderr, "[jade] %s grid %d x %d threads, smem %d, blocks/SM %d, frames %lld\n", kc.name, grid, kc.threads, kc.smem, kc.blocks_per_sm, frames);
     kernel_fn fn = (P.db && kc.fn_db) ? kc.fn_db : kc.fn;
     // long runs of evenly spaced columns, a quarter frame apart: the instantiation that walks contiguous columns per warp
     static const bool no_run = [] { const char* v = getenv("JADE_PK_LOAD"); return v && !strcmp(v, "norun"); }(); // experiments
+    static const long long run_min = [] { const char* v = getenv("JADE_RUN_MIN"); return v ? atoll(v) : 16ll; }(); // frames per warp that make a "long run"
     if (kc.fn_run && !no_run && P.hop == kc.run_hop && (P.fb == 1 ? P.bstride == P.hop : P.bstride == P.fb * P.hop) &&
-        frames >= 16ll * grid * kc.units_per_block)
+        frames >= run_min * grid * kc.units_per_block)
         fn = P.db ? kc.fn_run_db : kc.fn_run;
+    if (trace)
+        fprintf(stderr, "[jade] %s%s grid %d x %d threads, smem %d, blocks/SM %d, frames %lld\n", kc.name, (fn == kc.fn_run || fn == kc.fn_run_db) ? "+run" : "", grid,
+                kc.threads, kc.smem, kc.blocks_per_sm, frames);
     if (P.ring_w > 0) {
         // streaming push: programmatic dependent launch behind ingest_kernel (every STFT kernel calls grid_dep_wait()
         // after its table prologue, jade_kernels.cuh)

@@ -183,7 +183,7 @@ JADE_KERNEL(Pk3Cfg::THREADS, 2) stft_pk3_kernel(const KParams P)
         stream_ = (int)(gg / (unsigned)P.ncols);
         j_ = P.first_col + (gg - (unsigned)stream_ * (unsigned)P.ncols);
         st_ = frame_start(P, j_);
-        staged_ = LD == PK3_STAGED;
+        staged_ = LD == PK3_STAGED || (P.aligned4 && st_ >= 0 && st_ + N <= P.nsamples);
     };
     auto stage = [&](unsigned gg) { // after a __syncthreads(): the frame's 64 KB -> buf (thread 0; nothing for a boundary frame)
         int stream_;

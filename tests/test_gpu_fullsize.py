@@ -55,22 +55,24 @@ def _win_name(eng):
     return [k for k, v in O.WIN.items() if v == eng.cfg.window][0]
 
 
-def test_cfg2_batch_long_runs_tensor_memory_ring(gpu_engine_factory):
-    """The bench workload shape (stereo 48 kHz, FFT 2048, hop 512; 64 streams x 20 s = 120 k frames in one launch): launches this
-    long go to the PKZ_RING instantiation of stft_pkz2048_kernel (contiguous columns per warp, the frame's samples in a
-    tensor-memory ring, 4 KB TMA staging per frame).  Bit-identical to the same columns rendered in short launches (PKZ_ASYNC:
-    frames dealt round-robin, whole frames staged) -- i.e. runs that start anywhere, cross stream boundaries and include the
-    pre-roll columns -- plus spot parity against the oracle, the pre-roll colour and determinism."""
+@pytest.mark.parametrize("ch,hop,kernel", [(2, 512, "pkz2048"), (1, 512, "pk2048"), (1, 256, "pk2048")])
+def test_long_runs_tensor_memory_ring(gpu_engine_factory, ch, hop, kernel):
+    """The bench workload shape (stereo 48 kHz, FFT 2048, hop 512; 64 streams x 20 s = 120 k frames in one launch) and its mono
+    siblings: launches this long go to the long-run instantiations (PKZ_RING of stft_pkz2048_kernel, PK_LD_RING8 / RING4 of
+    stft_pk2048_kernel: contiguous columns per warp, the frame's samples in a tensor-memory ring, only the new chunk staged).
+    Bit-identical to the same columns rendered in short launches (frames dealt round-robin, whole frames staged) -- i.e. runs
+    that start anywhere, cross stream boundaries and include the pre-roll columns -- plus spot parity against the oracle, the
+    pre-roll colour and determinism."""
     import torch
-    fs, N, hop, S, n = 48000.0, 2048, 512, 64, 48000 * 20
+    fs, N, S, n = 48000.0, 2048, 64, 48000 * 20
     B = N // 2 + 1
-    eng = gpu_engine_factory(sample_rate=fs, fft_size=N, hop=hop, channels=2)
-    assert eng.kernel_name == "pkz2048"
+    eng = gpu_engine_factory(sample_rate=fs, fft_size=N, hop=hop, channels=ch)
+    assert eng.kernel_name == kernel
     ncols = eng.columns_for(n)
-    d_in = torch.empty((S, 2, n), dtype=torch.float32, device="cuda")
-    eng.synth_device(d_in.data_ptr(), S, 2, n, 2 * n, n, kind="mix", seed=2)
+    d_in = torch.empty((S, ch, n), dtype=torch.float32, device="cuda")
+    eng.synth_device(d_in.data_ptr(), S, ch, n, ch * n, n, kind="mix", seed=2)
     d_pix = torch.empty((S, ncols, B), dtype=torch.int32, device="cuda")
-    eng.render_device(d_in.data_ptr(), S, n, 2 * n, n, 0, ncols, d_pix.data_ptr(), None)
+    eng.render_device(d_in.data_ptr(), S, n, ch * n, n, 0, ncols, d_pix.data_ptr(), None)
     eng.sync()
     assert S * ncols >= 16 * 148 * 12, "the launch must be long enough for the ring instantiation"
     floor = int(_floor_pixel(eng).view(np.int32))
@@ -78,15 +80,15 @@ def test_cfg2_batch_long_runs_tensor_memory_ring(gpu_engine_factory):
     # short launches (two streams, a few hundred columns each: below the ring threshold) must reproduce it bit for bit
     d_part = torch.empty((2, 300, B), dtype=torch.int32, device="cuda")
     for s0, c0 in ((0, 0), (17, 911), (62, ncols - 300)):
-        eng.render_device(d_in[s0].data_ptr(), 2, n, 2 * n, n, c0, 300, d_part.data_ptr(), None)
+        eng.render_device(d_in[s0].data_ptr(), 2, n, ch * n, n, c0, 300, d_part.data_ptr(), None)
         eng.sync()
         assert torch.equal(d_part, d_pix[s0:s0 + 2, c0:c0 + 300]), f"ring rendering differs from short launches at stream {s0}, column {c0}"
     rng = np.random.default_rng(2)
     for _ in range(3):
         s, c0 = int(rng.integers(S)), int(rng.integers(8, ncols - 8))
-        _spot_check(eng, d_in[s], n, N, hop, c0, 6, d_pix[s, c0:c0 + 6], lambda db: db[:, ::-1], f"cfg2 stream {s}")
+        _spot_check(eng, d_in[s], n, N, hop, c0, 6, d_pix[s, c0:c0 + 6], lambda db: db[:, ::-1], f"stream {s}")
     first = _checksum(d_pix)
-    eng.render_device(d_in.data_ptr(), S, n, 2 * n, n, 0, ncols, d_pix.data_ptr(), None)
+    eng.render_device(d_in.data_ptr(), S, n, ch * n, n, 0, ncols, d_pix.data_ptr(), None)
     eng.sync()
     assert _checksum(d_pix) == first
 
