@@ -27,7 +27,7 @@
 // Reference lines replaced: Spectrogram.cpp:50-56,137-145 (framing, window, spectrum::power), :107 (dB), :634-647 +
 // CColorpalette.h:32-47 (pixel loop).
 #pragma once
-#include "jade_pk.cuh"
+#include "jade_pkz.cuh"
 #include "jade_tmem.cuh"
 
 namespace jade {
@@ -74,7 +74,7 @@ struct Pk3Cfg {
     static constexpr int TM_COLS = 256; // tensor memory per CTA: 128 columns per warp of a quadrant (window 64, pass-2 table 32, pass-3 table 32)
     static constexpr int off_row = 0;
     static constexpr int off_pal = off_row + M * 8;
-    static JADE_HD int off_bar(int npal) { return off_pal + (npal * 4 + 15) / 16 * 16; }
+    static JADE_HD int off_bar(int npal) { return off_pal + ((npal + 1) * 4 + 15) / 16 * 16; } // table + the `>= m_Max` entry (pkz_emit)
     static JADE_HD int smem_bytes(int npal) { return off_bar(npal) + 16; }
 };
 
@@ -124,7 +124,7 @@ JADE_KERNEL(Pk3Cfg::THREADS, 2) stft_pk3_kernel(const KParams P)
     const int c_lo = lane & 15, row2 = 4 * warp + 2 * (lane >> 4);
     const Pk3Lane L3 = pk3_lane(warp, lane);
 
-    for (int i = t; i < P.npal; i += Cfg::THREADS) s_pal[i] = P.palette[i];
+    for (int i = t; i <= P.npal; i += Cfg::THREADS) s_pal[i] = P.palette[i < P.npal ? i : P.ci_hi];
     if (t == 0) mbar_init(bar, 1);
     if (t < 32) tm_alloc(s_tm, Cfg::TM_COLS);
     tm_fence_before_sync();
@@ -316,25 +316,17 @@ JADE_KERNEL(Pk3Cfg::THREADS, 2) stft_pk3_kernel(const KParams P)
             const f2 Bv = sub2(zk, conj2(zp));
             const f2 T = cmul2(Bv, pk(hi(w), -lo(w)));
             const f2 xp = add2(A, T), xm = sub2(A, T);
-            const float plo = fm(lo(xp), lo(xp), JADE_FMUL(hi(xp), hi(xp)));
-            const float phi = fm(lo(xm), lo(xm), JADE_FMUL(hi(xm), hi(xm)));
-            const float ll = JADE_LOG2F(JADE_FADD(plo, 1e-11f)), lh = JADE_LOG2F(JADE_FADD(phi, 1e-11f));
+            // + 1e-11 (Spectrogram.cpp:36,107) rides on the power FMAs; dB, palette index by one FFMA and one integer clamp (pkz_emit)
+            const float plo = fm(lo(xp), lo(xp), fm(hi(xp), hi(xp), 1e-11f));
+            const float phi = fm(lo(xm), lo(xm), fm(hi(xm), hi(xm), 1e-11f));
             const int k = (q < 8 ? kb_lo : kb_hi) + 512 * q;
-            if (WANT_DB && o.db) {
-                o.db[k] = JADE_FMUL(3.01029995663981195f, ll);
-                o.db[M - k] = JADE_FMUL(3.01029995663981195f, lh);
-            }
-            if (o.pix) {
-                o.pix[M - k] = colour_of_lg(ll, P, s_pal); // bin k -> row M - k
-                o.pix[k] = colour_of_lg(lh, P, s_pal);
-            }
+            pkz_emit<WANT_DB>(plo, o.pix ? o.pix + (M - k) : nullptr, (WANT_DB && o.db) ? o.db + k : nullptr, P, s_pal); // bin k -> row M - k
+            pkz_emit<WANT_DB>(phi, o.pix ? o.pix + k : nullptr, (WANT_DB && o.db) ? o.db + (M - k) : nullptr, P, s_pal);
         }
         if (L3.self) { // bin M/2 (self-paired, A[8] of that lane): X = 2 conj Z
             const float a = lo(ua[8]), b = hi(ua[8]);
-            const float p = fm(JADE_FMUL(4.0f, a), a, JADE_FMUL(JADE_FMUL(4.0f, b), b));
-            const float lg = JADE_LOG2F(JADE_FADD(p, 1e-11f));
-            if (WANT_DB && o.db) o.db[M / 2] = JADE_FMUL(3.01029995663981195f, lg);
-            if (o.pix) o.pix[M / 2] = colour_of_lg(lg, P, s_pal);
+            const float p = fm(JADE_FMUL(4.0f, a), a, fm(JADE_FMUL(4.0f, b), b, 1e-11f));
+            pkz_emit<WANT_DB>(p, o.pix ? o.pix + M / 2 : nullptr, (WANT_DB && o.db) ? o.db + M / 2 : nullptr, P, s_pal);
         }
     }
     tm_fence_before_sync();
