@@ -27,6 +27,8 @@
 // Reference lines replaced: Spectrogram.cpp:50-56,137-145 (framing, window, spectrum::power), :107 (dB), :634-647 +
 // CColorpalette.h:32-47 (pixel loop).
 #pragma once
+#include <type_traits>
+
 #include "jade_pkz.cuh"
 #include "jade_tmem.cuh"
 
@@ -303,26 +305,37 @@ JADE_KERNEL(Pk3Cfg::THREADS, 2) stft_pk3_kernel(const KParams P)
         const ColOut o = col_out(P, stream, j);
         const f2* ua = v;
         const f2* ub = v + 16;
-        // (the self-pairing lane -- kappa = 8, lane 0: rows (0, 0) and (0, 8) -- pairs A[q] with A[16 - q] in its slots q < 8 and B[q - 8]
-        // with B[23 - q] in its slots q >= 8; selects in every thread: a warp-uniform branch around a re-sort of that warp's
-        // registers costs spills and 6 %)
+        // The self-pairing lane -- kappa = 8, lane 0 of warp 4: rows (0, 0) and (0, 8) -- pairs A[q] with A[16 - q] in its slots q < 8
+        // and B[q - 8] with B[23 - q] in its slots q >= 8.  Two copies of the loop behind a warp-uniform branch: only warp 4 executes
+        // the selects (48 per thread and frame).  (A re-sort of that warp's registers in front of ONE loop costs spills and 6 %.)
+        auto split_emit = [&](auto self_warp) {
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-            f2 zk = ua[q], zp = ub[15 - q];
-            if (q >= 8) zk = sel2(L3.self, ub[q - 8], zk);
-            zp = sel2(L3.self, q < 8 ? ua[(16 - q) & 15] : ub[23 - q], zp);
-            const f2 w = cmul2(q < 8 ? ws_lo : ws_hi, pk(cos32(q), -sin32(q))); // W_N^k ; -i W_N^k = (w.y, -w.x)
-            const f2 A = add2(zk, conj2(zp));
-            const f2 Bv = sub2(zk, conj2(zp));
-            const f2 T = cmul2(Bv, pk(hi(w), -lo(w)));
-            const f2 xp = add2(A, T), xm = sub2(A, T);
-            // + 1e-11 (Spectrogram.cpp:36,107) rides on the power FMAs; dB, palette index by one FFMA and one integer clamp (pkz_emit)
-            const float plo = fm(lo(xp), lo(xp), fm(hi(xp), hi(xp), 1e-11f));
-            const float phi = fm(lo(xm), lo(xm), fm(hi(xm), hi(xm), 1e-11f));
-            const int k = (q < 8 ? kb_lo : kb_hi) + 512 * q;
-            pkz_emit<WANT_DB>(plo, o.pix ? o.pix + (M - k) : nullptr, (WANT_DB && o.db) ? o.db + k : nullptr, P, s_pal); // bin k -> row M - k
-            pkz_emit<WANT_DB>(phi, o.pix ? o.pix + k : nullptr, (WANT_DB && o.db) ? o.db + (M - k) : nullptr, P, s_pal);
-        }
+            for (int q = 0; q < 16; ++q) {
+                f2 zk = ua[q], zp = ub[15 - q];
+                f2 wb = q < 8 ? ws_lo : ws_hi;
+                int kb = q < 8 ? kb_lo : kb_hi;
+                if constexpr (decltype(self_warp)::value) {
+                    if (q >= 8) zk = sel2(L3.self, ub[q - 8], zk);
+                    zp = sel2(L3.self, q < 8 ? ua[(16 - q) & 15] : ub[23 - q], zp);
+                } else {
+                    wb = ws_lo; // (regular lanes: ws_hi == ws_lo, kb_hi == kb_lo)
+                    kb = kb_lo;
+                }
+                const f2 w = cmul2(wb, pk(cos32(q), -sin32(q))); // W_N^k ; -i W_N^k = (w.y, -w.x)
+                const f2 A = add2(zk, conj2(zp));
+                const f2 Bv = sub2(zk, conj2(zp));
+                const f2 T = cmul2(Bv, pk(hi(w), -lo(w)));
+                const f2 xp = add2(A, T), xm = sub2(A, T);
+                // + 1e-11 (Spectrogram.cpp:36,107) rides on the power FMAs; dB, palette index by one FFMA and one integer clamp (pkz_emit)
+                const float plo = fm(lo(xp), lo(xp), fm(hi(xp), hi(xp), 1e-11f));
+                const float phi = fm(lo(xm), lo(xm), fm(hi(xm), hi(xm), 1e-11f));
+                const int k = kb + 512 * q;
+                pkz_emit<WANT_DB>(plo, o.pix ? o.pix + (M - k) : nullptr, (WANT_DB && o.db) ? o.db + k : nullptr, P, s_pal); // bin k -> row M - k
+                pkz_emit<WANT_DB>(phi, o.pix ? o.pix + k : nullptr, (WANT_DB && o.db) ? o.db + (M - k) : nullptr, P, s_pal);
+            }
+        };
+        if (warp == 4) split_emit(std::true_type{});
+        else split_emit(std::false_type{});
         if (L3.self) { // bin M/2 (self-paired, A[8] of that lane): X = 2 conj Z
             const float a = lo(ua[8]), b = hi(ua[8]);
             const float p = fm(JADE_FMUL(4.0f, a), a, fm(JADE_FMUL(4.0f, b), b, 1e-11f));
