@@ -525,6 +525,12 @@ void fill_params(jade_engine* e, KParams& P)
     P.hop = c.hop;
     P.fb = c.frames_per_block;
     P.bstride = c.block_stride;
+    if (c.frames_per_block > 1 && (long long)c.block_stride == (long long)c.frames_per_block * c.hop) {
+        // evenly spaced columns (every reference geometry but perc10): one column per "block" of hop samples, so that
+        // frame_start() in the kernels is a multiply-add instead of a 64-bit division and modulo per frame
+        P.fb = 1;
+        P.bstride = c.hop;
+    }
     P.preroll = c.preroll;
     P.channels = c.channels;
     P.mix_mode = c.mix_mode;

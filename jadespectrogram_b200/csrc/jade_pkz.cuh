@@ -324,7 +324,7 @@ JADE_KERNEL(PkzCfg::WARPS * 32, 1) stft_pkz2048_kernel(const KParams P)
         const ColOut o = col_out(P, (int)cur.stream, P.first_col + cur.col);
         // ---- samples x window, stage 1 (the frame was staged while the previous one was in pass 2)
         f2 v[64];
-        if (STAGED) {
+        if (STAGED && !RING) {
             mbar_wait(bar, copies & 1u);
             ++copies;
         }
@@ -332,33 +332,50 @@ JADE_KERNEL(PkzCfg::WARPS * 32, 1) stft_pkz2048_kernel(const KParams P)
             long long st;
             const float* c0 = frame_ptr(cur, st);
             if constexpr (RING) {
+                // Eight pairs at a time: samples n1 = 8 c .. + 7 (slot of chunk c >> 1) and 32 + 8 c .. + 7 (chunk (c >> 1) + 2), window
+                // chunk c.  Order c = 2, 3, 0, 1: the NEW chunk (3 = the high samples of c = 2, 3) is consumed from the registers that
+                // carry it from shared to tensor memory (no store -> wait -> load round trip in front of the arithmetic), and the
+                // tensor-memory loads of c = 2 are in flight before the mbarrier wait.
+                uint32_t xa[2][16], xb[2][16], wq[2][16], xs[32];
+                auto fetch = [&](int c, bool hi) {
+                    tm_ld<16>(tring + 32 * ((ring + (c >> 1)) & 3u) + 16 * (c & 1), xa[c & 1]);
+                    if (hi) tm_ld<16>(tring + 32 * ((ring + (c >> 1) + 2) & 3u) + 16 * (c & 1), xb[c & 1]);
+                    tm_ld<16>(tq + 64 + 16 * c, wq[c & 1]);
+                };
                 if (!warm) {
+                    mbar_wait(bar, copies & 1u);
                     ring = 0;
                     ingest(0);
                     ingest(1);
                     ingest(2);
+                    tm_wait_st();
+                    fetch(2, false);
+                } else {
+                    fetch(2, false);
+                    mbar_wait(bar, copies & 1u);
                 }
-                ingest(3);
-                tm_wait_st();
-                // eight pairs at a time: samples n1 = 8 c .. + 7 (slot of chunk c >> 1) and 32 + 8 c .. + 7 (chunk (c >> 1) + 2), window chunk c
-                uint32_t xa[2][16], xb[2][16], wq[2][16];
-                auto fetch = [&](int c) {
-                    tm_ld<16>(tring + 32 * ((ring + (c >> 1)) & 3u) + 16 * (c & 1), xa[c & 1]);
-                    tm_ld<16>(tring + 32 * ((ring + (c >> 1) + 2) & 3u) + 16 * (c & 1), xb[c & 1]);
-                    tm_ld<16>(tq + 64 + 16 * c, wq[c & 1]);
-                };
-                fetch(0);
+                ++copies;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
+                for (int i = 0; i < 16; ++i) {
+                    xs[2 * i] = f2u(x0[32 * (48 + i)]);
+                    xs[2 * i + 1] = f2u(x1[32 * (48 + i)]);
+                }
+                tm_st<32>(tring + 32 * ((ring + 3) & 3u), xs);
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) {
+                    const int c = (cc + 2) & 3;
                     tm_wait_ld<16>(xa[c & 1]);
-                    tm_tie<16>(xb[c & 1]);
+                    if (c < 2) tm_tie<16>(xb[c & 1]);
                     tm_tie<16>(wq[c & 1]);
-                    if (c < 3) fetch(c + 1);
+                    if (cc < 3) fetch((c + 1) & 3, cc >= 1);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        win_stage1_64(v, 8 * c + i, pk(u2f(xa[c & 1][2 * i]), u2f(xa[c & 1][2 * i + 1])), u2f(wq[c & 1][i]),
-                                      pk(u2f(xb[c & 1][2 * i]), u2f(xb[c & 1][2 * i + 1])), u2f(wq[c & 1][8 + i]));
+                    for (int i = 0; i < 8; ++i) {
+                        const f2 hi_s = c < 2 ? pk(u2f(xb[c & 1][2 * i]), u2f(xb[c & 1][2 * i + 1]))
+                                              : pk(u2f(xs[16 * (c & 1) + 2 * i]), u2f(xs[16 * (c & 1) + 2 * i + 1]));
+                        win_stage1_64(v, 8 * c + i, pk(u2f(xa[c & 1][2 * i]), u2f(xa[c & 1][2 * i + 1])), u2f(wq[c & 1][i]), hi_s, u2f(wq[c & 1][8 + i]));
+                    }
                 }
+                tm_wait_st(); // (the slot is read again by the next frame of this warp)
                 ring = (ring + 1) & 3u;
             } else if constexpr (Cfg::TM) {
                 // window chunk c (n1 = 8 c .. + 7 and 32 + 8 c .. + 7) comes back from tensor memory while chunk c - 1 is consumed
