@@ -259,14 +259,14 @@ int choose_kernel(jade_engine* e)
         case 4: return jade::PkSmallCfg<4>::smem_bytes(e->npal);
         case 8: return jade::PkSmallCfg<8>::smem_bytes(e->npal);
         case 16: return jade::PkSmallCfg<16>::smem_bytes(e->npal);
-        default: return jade::PkCfg::smem_bytes(e->npal);
+        default: return mu == jade::MIX_NONE ? jade::PkCfgFor<jade::MIX_NONE>::smem_bytes(e->npal) : jade::PkCfg::smem_bytes(e->npal);
         }
     };
     if (N >= 128 && N <= 2048 && !po && mu != jade::MIX_SEL && pk_smem(N / 64) <= e->smem_optin) {
         // fast path: packed-FP32x2 kernels (jade_pk.cuh for N = 2048, jade_pk_small.cuh below)
         const int T = N / 64;
         kc.family = 3;
-        int warps = jade::PkCfg::WARPS;
+        int warps = mu == jade::MIX_NONE ? jade::PkCfgFor<jade::MIX_NONE>::WARPS : jade::PkCfg::WARPS;
         switch (T) {
         case 2: warps = jade::PkSmallCfg<2>::WARPS; break;
         case 4: warps = jade::PkSmallCfg<4>::WARPS; break;
@@ -281,7 +281,7 @@ int choose_kernel(jade_engine* e)
         case 4: kc.smem = jade::PkSmallCfg<4>::smem_bytes(e->npal); break;
         case 8: kc.smem = jade::PkSmallCfg<8>::smem_bytes(e->npal); break;
         case 16: kc.smem = jade::PkSmallCfg<16>::smem_bytes(e->npal); break;
-        default: kc.smem = jade::PkCfg::smem_bytes(e->npal); break;
+        default: kc.smem = pk_smem(32); break;
         }
         if (T == 32) snprintf(kc.name, sizeof kc.name, "pk2048");
         else snprintf(kc.name, sizeof kc.name, "pksmall<%d>", T);
@@ -465,6 +465,9 @@ int choose_kernel(jade_engine* e)
     // takes 256 of the 512 tensor-memory columns and two of its CTAs do share an SM -- launch__waves_per_multiprocessor in
     // profiles/r02c_pk3_16384.txt)
     if ((kc.family == 3 || kc.family == 1) && N == 16384 && kc.threads == jade::Pk3Cfg::THREADS && kc.smem == jade::Pk3Cfg::smem_bytes(e->npal)) kc.blocks_per_sm = 2;
+    if (const char* v = getenv("JADE_BLOCKS_PER_SM")) { // experiments (kernels with tcgen05.alloc: the query above answers 1)
+        if (atoi(v) > 0) kc.blocks_per_sm = e->kc_edge.blocks_per_sm = atoi(v);
+    }
     if (kc.family == 4) {
         // how many clusters fit at once (GPCs with an odd number of SMs leave one unpaired): the persistent grid is exactly that
         cudaLaunchConfig_t lc = {};

@@ -454,9 +454,15 @@ JADE_DEVICE void fft32_twisted_hi(f2* u, const uint32_t* r)
 #ifndef JADE_PK_CTAS
 #define JADE_PK_CTAS 1
 #endif
-struct PkCfg {
+// one contributing channel (MIX_NONE): 32 complex values per lane fit 128 registers, so 16 warps share the SM (+2..3 % over 12,
+// gpurun_out/ab2.txt); the mixing instantiations carry the accumulators as well and spill at 128 (12 warps x 168 registers)
+#ifndef JADE_PK_WARPS_MONO
+#define JADE_PK_WARPS_MONO 16
+#endif
+template <int W>
+struct PkCfgW {
     static constexpr int M = 1024, N = 2048, B = 1025;
-    static constexpr int WARPS = JADE_PK_WARPS;
+    static constexpr int WARPS = W;
     static constexpr int ROW = 34;   // f2 words per lane row of the window table (32 + 16 B pad)
     static constexpr int TROW = 18;  // f2 words per lane row of the twisted pass-2 table (16 + 16 B pad)
     static constexpr int PROW = 18;  // f2 words per lane row of the split-twiddle table (16 + 16 B pad)
@@ -478,6 +484,9 @@ struct PkCfg {
     static JADE_HD int off_xch(int npal) { return off_bar(npal) + (WARPS * 8 + 8 + 15) / 16 * 16; }
     static JADE_HD int smem_bytes(int npal) { return off_xch(npal) + WARPS * XCH * 8; }
 };
+using PkCfg = PkCfgW<JADE_PK_WARPS>;
+template <int MIXK>
+using PkCfgFor = PkCfgW<(MIXK == MIX_NONE && JADE_PK_CTAS == 1) ? JADE_PK_WARPS_MONO : JADE_PK_WARPS>;
 
 // How a frame reaches the registers:
 //   PK_LD_ASYNC  : frames lie inside [0, nsamples) and start on a multiple of 4 samples with 16-byte aligned channel
@@ -542,14 +551,14 @@ template <int MIXK, bool WANT_DB, int LD>
 #if defined(JADE_PK_MAXREG) && !defined(JADE_EMU)
 __global__ void __maxnreg__(JADE_PK_MAXREG) stft_pk2048_kernel(const KParams P)
 #else
-JADE_KERNEL(PkCfg::WARPS * 32, JADE_PK_CTAS) stft_pk2048_kernel(const KParams P)
+JADE_KERNEL(PkCfgFor<MIXK>::WARPS * 32, JADE_PK_CTAS) stft_pk2048_kernel(const KParams P)
 #endif
 {
-    using Cfg = PkCfg;
+    using Cfg = PkCfgFor<MIXK>;
     constexpr int M = Cfg::M;
     constexpr bool RING = LD == PK_LD_RING4 || LD == PK_LD_RING8, STAGED = LD == PK_LD_ASYNC || RING;
     constexpr int CH = LD == PK_LD_RING8 ? 8 : 4, NCH = 32 / CH; // ring: NCH chunks of CH values n1 (hop = 64 CH samples)
-    static_assert(!RING || (Cfg::TM && MIXK == MIX_NONE && Cfg::WARPS <= 12), "the sample ring: tensor memory, one contributing channel");
+    static_assert(!RING || (Cfg::TM && MIXK == MIX_NONE && Cfg::WARPS <= 24), "the sample ring: tensor memory, one contributing channel");
     JADE_DYN_SMEM(smem);
     char* sm = reinterpret_cast<char*>(smem);
     f2* s_win = reinterpret_cast<f2*>(sm + Cfg::off_win);

@@ -49,7 +49,7 @@ void run_cta(const KParams& P, int mixk, bool general, int grid)
 template <int T, int MIXK, bool WDB, bool GUARD>
 void run_pk_one(const KParams& P, int npal, int grid)
 {
-    const int block = (T == 32 ? jade::PkCfg::WARPS : jade::PkSmallCfg<(T == 32 ? 16 : T)>::WARPS) * 32;
+    const int block = (T == 32 ? jade::PkCfgFor<MIXK>::WARPS : jade::PkSmallCfg<(T == 32 ? 16 : T)>::WARPS) * 32;
     if constexpr (T == 32) {
         // same routing as launch_stft: AbsMean over two channels -> the one-complex-transform kernel (jade_pkz.cuh) for
         // every column (TMA-staged when 16-byte aligned and interior, guarded otherwise) unless JADE_EMU_NOPAIR is set
@@ -62,15 +62,15 @@ void run_pk_one(const KParams& P, int npal, int grid)
             else if (getenv("JADE_EMU_RING")) jade_emu::launch(jade::stft_pkz2048_kernel<WDB, jade::PKZ_RING>, grid, zb, zs, P); // launch_one: long evenly spaced runs
             else jade_emu::launch(jade::stft_pkz2048_kernel<WDB, jade::PKZ_ASYNC>, grid, zb, zs, P);
         }
-        else if (GUARD) jade_emu::launch(jade::stft_pk2048_kernel<MIXK, WDB, jade::PK_LD_GUARD>, grid, block, jade::PkCfg::smem_bytes(npal), P);
+        else if (GUARD) jade_emu::launch(jade::stft_pk2048_kernel<MIXK, WDB, jade::PK_LD_GUARD>, grid, block, jade::PkCfgFor<MIXK>::smem_bytes(npal), P);
         else if (P.aligned4 && pair_ok)
             jade_emu::launch(jade::stft_pk2048x2_kernel<WDB>, grid, jade::PkPairCfg::WARPS * 32, jade::PkPairCfg::smem_bytes(npal), P);
         else if (P.aligned4 && MIXK == jade::MIX_NONE && getenv("JADE_EMU_RING") && (P.hop == 256 || P.hop == 512)) { // launch_one: long evenly spaced runs
-            if (P.hop == 256) jade_emu::launch(jade::stft_pk2048_kernel<jade::MIX_NONE, WDB, jade::PK_LD_RING4>, grid, block, jade::PkCfg::smem_bytes(npal), P);
-            else jade_emu::launch(jade::stft_pk2048_kernel<jade::MIX_NONE, WDB, jade::PK_LD_RING8>, grid, block, jade::PkCfg::smem_bytes(npal), P);
+            if (P.hop == 256) jade_emu::launch(jade::stft_pk2048_kernel<jade::MIX_NONE, WDB, jade::PK_LD_RING4>, grid, block, jade::PkCfgFor<MIXK>::smem_bytes(npal), P);
+            else jade_emu::launch(jade::stft_pk2048_kernel<jade::MIX_NONE, WDB, jade::PK_LD_RING8>, grid, block, jade::PkCfgFor<MIXK>::smem_bytes(npal), P);
         }
-        else if (P.aligned4) jade_emu::launch(jade::stft_pk2048_kernel<MIXK, WDB, jade::PK_LD_ASYNC>, grid, block, jade::PkCfg::smem_bytes(npal), P);
-        else jade_emu::launch(jade::stft_pk2048_kernel<MIXK, WDB, jade::PK_LD_DIRECT>, grid, block, jade::PkCfg::smem_bytes(npal), P);
+        else if (P.aligned4) jade_emu::launch(jade::stft_pk2048_kernel<MIXK, WDB, jade::PK_LD_ASYNC>, grid, block, jade::PkCfgFor<MIXK>::smem_bytes(npal), P);
+        else jade_emu::launch(jade::stft_pk2048_kernel<MIXK, WDB, jade::PK_LD_DIRECT>, grid, block, jade::PkCfgFor<MIXK>::smem_bytes(npal), P);
     }
     else jade_emu::launch(jade::stft_pksmall_kernel<T, MIXK, WDB, GUARD>, grid, block, jade::PkSmallCfg<T>::smem_bytes(npal), P);
 }
