@@ -253,12 +253,13 @@ int choose_kernel(jade_engine* e)
     // Every kernel keeps the palette in shared memory, so a long table can push an instantiation over the opt-in limit.
     // Degrade instead of failing: two-channel complex kernel -> per-channel packed kernels -> general kernels; only when
     // nothing fits does configuration / jade_set_palette fail (and jade_set_palette then restores the previous table).
+    const bool mono = mu == jade::MIX_NONE;
     auto pk_smem = [&](int T) {
         switch (T) {
-        case 2: return jade::PkSmallCfg<2>::smem_bytes(e->npal);
-        case 4: return jade::PkSmallCfg<4>::smem_bytes(e->npal);
-        case 8: return jade::PkSmallCfg<8>::smem_bytes(e->npal);
-        case 16: return jade::PkSmallCfg<16>::smem_bytes(e->npal);
+        case 2: return mono ? jade::PkSmallCfg<2, true>::smem_bytes(e->npal) : jade::PkSmallCfg<2>::smem_bytes(e->npal);
+        case 4: return mono ? jade::PkSmallCfg<4, true>::smem_bytes(e->npal) : jade::PkSmallCfg<4>::smem_bytes(e->npal);
+        case 8: return mono ? jade::PkSmallCfg<8, true>::smem_bytes(e->npal) : jade::PkSmallCfg<8>::smem_bytes(e->npal);
+        case 16: return mono ? jade::PkSmallCfg<16, true>::smem_bytes(e->npal) : jade::PkSmallCfg<16>::smem_bytes(e->npal);
         default: return mu == jade::MIX_NONE ? jade::PkCfgFor<jade::MIX_NONE>::smem_bytes(e->npal) : jade::PkCfg::smem_bytes(e->npal);
         }
     };
@@ -268,19 +269,19 @@ int choose_kernel(jade_engine* e)
         kc.family = 3;
         int warps = mu == jade::MIX_NONE ? jade::PkCfgFor<jade::MIX_NONE>::WARPS : jade::PkCfg::WARPS;
         switch (T) {
-        case 2: warps = jade::PkSmallCfg<2>::WARPS; break;
-        case 4: warps = jade::PkSmallCfg<4>::WARPS; break;
-        case 8: warps = jade::PkSmallCfg<8>::WARPS; break;
-        case 16: warps = jade::PkSmallCfg<16>::WARPS; break;
+        case 2: warps = mono ? jade::PkSmallCfg<2, true>::WARPS : jade::PkSmallCfg<2>::WARPS; break;
+        case 4: warps = mono ? jade::PkSmallCfg<4, true>::WARPS : jade::PkSmallCfg<4>::WARPS; break;
+        case 8: warps = mono ? jade::PkSmallCfg<8, true>::WARPS : jade::PkSmallCfg<8>::WARPS; break;
+        case 16: warps = mono ? jade::PkSmallCfg<16, true>::WARPS : jade::PkSmallCfg<16>::WARPS; break;
         default: break;
         }
         kc.threads = warps * 32;
         kc.units_per_block = warps * (32 / T);
         switch (T) {
-        case 2: kc.smem = jade::PkSmallCfg<2>::smem_bytes(e->npal); break;
-        case 4: kc.smem = jade::PkSmallCfg<4>::smem_bytes(e->npal); break;
-        case 8: kc.smem = jade::PkSmallCfg<8>::smem_bytes(e->npal); break;
-        case 16: kc.smem = jade::PkSmallCfg<16>::smem_bytes(e->npal); break;
+        case 2: kc.smem = pk_smem(2); break;
+        case 4: kc.smem = pk_smem(4); break;
+        case 8: kc.smem = pk_smem(8); break;
+        case 16: kc.smem = pk_smem(16); break;
         default: kc.smem = pk_smem(32); break;
         }
         if (T == 32) snprintf(kc.name, sizeof kc.name, "pk2048");

@@ -76,7 +76,9 @@ JADE_HD int twr_exponent(int k1, int t)
     return (R / LEN) * (k1 + 32 * J);
 }
 
-template <int T>
+// MONO (one contributing channel, MIX_NONE): no channel accumulators, the kernel fits 128 registers and 16 warps share the SM
+// for N = 512 / 1024 (cfg1 +3 %, gpurun_out/ab3.txt); the mixing instantiations spill at 128 and stay at 12 warps
+template <int T, bool MONO = false>
 struct PkSmallCfg {
     static constexpr int M = 32 * T, N = 2 * M, B = M + 1;
     static constexpr int F = 32 / T;
@@ -84,7 +86,7 @@ struct PkSmallCfg {
 #if defined(JADE_PKS_WARPS) && defined(JADE_PKS_CTAS)
     static constexpr int WARPS = JADE_PKS_WARPS, CTAS = JADE_PKS_CTAS;
 #else
-    static constexpr int WARPS = (T >= 8) ? 12 : 8, CTAS = (T >= 8) ? 1 : 2;
+    static constexpr int WARPS = (T >= 8) ? (MONO ? 16 : 12) : 8, CTAS = (T >= 8) ? 1 : 2;
 #endif
     static constexpr int ROW = 34;    // f2 words per s-row of the window / inter-pass twiddle tables (32 + 16 B pad)
     static constexpr int PROW = 18;   // f2 words per s-row of the split-twiddle table (16 + 16 B pad)
@@ -112,9 +114,9 @@ JADE_HD constexpr int lane0_partner(int q)
 }
 
 template <int T, int MIXK, bool WANT_DB, bool GUARD>
-JADE_KERNEL(PkSmallCfg<T>::WARPS * 32, PkSmallCfg<T>::CTAS) stft_pksmall_kernel(const KParams P)
+JADE_KERNEL((PkSmallCfg<T, MIXK == MIX_NONE>::WARPS * 32), (PkSmallCfg<T, MIXK == MIX_NONE>::CTAS)) stft_pksmall_kernel(const KParams P)
 {
-    using Cfg = PkSmallCfg<T>;
+    using Cfg = PkSmallCfg<T, MIXK == MIX_NONE>;
     constexpr int M = Cfg::M, F = Cfg::F, H = Cfg::H, FS = Cfg::FS, TS = T + 1;
     static_assert(T >= 2 && T <= 16, "T = 32 is jade_pk.cuh");
     JADE_DYN_SMEM(smem);

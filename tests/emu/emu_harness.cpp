@@ -49,7 +49,7 @@ void run_cta(const KParams& P, int mixk, bool general, int grid)
 template <int T, int MIXK, bool WDB, bool GUARD>
 void run_pk_one(const KParams& P, int npal, int grid)
 {
-    const int block = (T == 32 ? jade::PkCfgFor<MIXK>::WARPS : jade::PkSmallCfg<(T == 32 ? 16 : T)>::WARPS) * 32;
+    const int block = (T == 32 ? jade::PkCfgFor<MIXK>::WARPS : jade::PkSmallCfg<(T == 32 ? 16 : T), MIXK == jade::MIX_NONE>::WARPS) * 32;
     if constexpr (T == 32) {
         // same routing as launch_stft: AbsMean over two channels -> the one-complex-transform kernel (jade_pkz.cuh) for
         // every column (TMA-staged when 16-byte aligned and interior, guarded otherwise) unless JADE_EMU_NOPAIR is set
@@ -72,7 +72,7 @@ void run_pk_one(const KParams& P, int npal, int grid)
         else if (P.aligned4) jade_emu::launch(jade::stft_pk2048_kernel<MIXK, WDB, jade::PK_LD_ASYNC>, grid, block, jade::PkCfgFor<MIXK>::smem_bytes(npal), P);
         else jade_emu::launch(jade::stft_pk2048_kernel<MIXK, WDB, jade::PK_LD_DIRECT>, grid, block, jade::PkCfgFor<MIXK>::smem_bytes(npal), P);
     }
-    else jade_emu::launch(jade::stft_pksmall_kernel<T, MIXK, WDB, GUARD>, grid, block, jade::PkSmallCfg<T>::smem_bytes(npal), P);
+    else jade_emu::launch(jade::stft_pksmall_kernel<T, MIXK, WDB, GUARD>, grid, block, jade::PkSmallCfg<T, MIXK == jade::MIX_NONE>::smem_bytes(npal), P);
 }
 template <int T>
 void run_pk(const KParams& P, int mixk, bool wdb, bool guard, int npal, int grid)
