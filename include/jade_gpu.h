@@ -158,7 +158,8 @@ int jade_push_samples(jade_engine* e, const float* const* planar, int nch, int n
  * like the reference's ring overwrite) into pixels[ncols][rows] and, if not NULL, db[ncols][bins].  *first_col is
  * the absolute index of the first returned column.  Returns when those columns are complete: pixel-only fetches of
  * freshly pushed columns poll the pinned, device-mapped ring (no wait for kernel retirement), everything else waits for
- * the GPU work of earlier pushes. */
+ * the GPU work of earlier pushes.  (Invariant behind the poll: both pixel formats bake the alpha byte 0xFF into every
+ * pixel, so a zeroed slot is "not written yet"; a pixel format that can produce 0 must take the waiting path.) */
 int jade_fetch_columns(jade_engine* e, uint32_t* pixels, float* db, int max_cols, int* ncols, int64_t* first_col);
 int jade_ring_info(jade_engine* e, int* ring_columns, int* rows, int* bins, int64_t* total_columns);
 /* Re-colour the whole ring from the stored dB values with the current palette/range (m_recomputeAll path,
