@@ -41,6 +41,7 @@ typedef void (*kernel_fn)(const KParams);
 struct KernelChoice {
     kernel_fn fn = nullptr;
     kernel_fn fn_db = nullptr; // variant that also stores the float dB column (only where the two differ)
+    kernel_fn fn_u8 = nullptr, fn_run_u8 = nullptr;  // pixel-only variants for palettes with KParams::pal_u8 (identical colours, no clamp instruction)
     kernel_fn fn_run = nullptr, fn_run_db = nullptr; // variant for long runs of evenly spaced columns run_hop samples apart (tensor-memory sample ring)
     int run_hop = 0;
     int threads = 0;
@@ -68,7 +69,9 @@ kernel_fn pk2048_kernel(int mixk, bool want_db, int load);        // jade_k_pk.c
 kernel_fn pk2048x2_kernel(bool want_db);                           // jade_k_pk2.cu (stereo: two real transforms per warp; experiments)
 kernel_fn pkz2048_kernel(bool want_db, bool guard);                // jade_k_pkz.cu (stereo: one complex transform per frame)
 kernel_fn pkz2048_run_kernel(bool want_db);
+kernel_fn pkz2048_u8_kernel(bool run);
 kernel_fn pk2048_run_kernel(bool want_db, int hop);                // jade_k_pk2.cu (one channel, hop 256 / 512: tensor-memory sample ring)
+kernel_fn pk3_u8_kernel();
 kernel_fn pk3_kernel(bool want_db, bool guard);                    // jade_k_pk3.cu (N = 16384, one contributing channel: three register passes)
 kernel_fn pksmall_kernel(int T, int mixk, bool want_db, bool guard); // jade_k_pksmall_a.cu / _b.cu
 } // namespace jade_k
@@ -337,6 +340,8 @@ int choose_kernel(jade_engine* e)
                     ke = kp;
                     kp.fn_run = jade_k::pkz2048_run_kernel(false);
                     kp.fn_run_db = jade_k::pkz2048_run_kernel(true);
+                    kp.fn_u8 = jade_k::pkz2048_u8_kernel(false);
+                    kp.fn_run_u8 = jade_k::pkz2048_u8_kernel(true);
                     kp.run_hop = 512;
                     snprintf(ke.name, sizeof ke.name, "pkz2048-guard");
                     ke.fn = jade_k::pkz2048_kernel(true, true);
@@ -344,6 +349,8 @@ int choose_kernel(jade_engine* e)
                 }
                 CU(e, cudaFuncSetAttribute((const void*)kp.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.smem));
                 CU(e, cudaFuncSetAttribute((const void*)kp.fn_db, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.smem));
+                for (kernel_fn f : {kp.fn_u8, kp.fn_run_u8})
+                    if (f) CU(e, cudaFuncSetAttribute((const void*)f, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.smem));
                 if (kp.fn_run) {
                     CU(e, cudaFuncSetAttribute((const void*)kp.fn_run, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.smem));
                     CU(e, cudaFuncSetAttribute((const void*)kp.fn_run_db, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.smem));
@@ -394,6 +401,8 @@ int choose_kernel(jade_engine* e)
         snprintf(ke.name, sizeof ke.name, "pk3<16384>-guard");
         kc.fn = jade_k::pk3_kernel(false, false);
         kc.fn_db = jade_k::pk3_kernel(true, false);
+        kc.fn_u8 = jade_k::pk3_u8_kernel();
+        CU(e, cudaFuncSetAttribute((const void*)kc.fn_u8, cudaFuncAttributeMaxDynamicSharedMemorySize, kc.smem));
         ke.fn = jade_k::pk3_kernel(true, true);
         ke.fn_db = nullptr;
         CU(e, cudaFuncSetAttribute((const void*)kc.fn_db, cudaFuncAttributeMaxDynamicSharedMemorySize, kc.smem));
@@ -402,6 +411,7 @@ int choose_kernel(jade_engine* e)
         e->kc_edge = ke;
         if (getenv("JADE_N16384") && !strcmp(getenv("JADE_N16384"), "mixed")) { // experiment: one launch, staged / guarded decided per frame
             kc.family = 1;
+            kc.fn_u8 = nullptr;
             kc.fn = jade_k::pk3_kernel(false, true);
             kc.fn_db = jade_k::pk3_kernel(true, true);
             CU(e, cudaFuncSetAttribute((const void*)kc.fn_db, cudaFuncAttributeMaxDynamicSharedMemorySize, kc.smem));
@@ -550,6 +560,8 @@ void fill_params(jade_engine* e, KParams& P)
     P.pmaxc = e->range.maxclamp();
     P.pmult = e->range.mult;
     jade::colour_fold(P);
+    // 256 colours and the `>= m_Max` colour equal to the last one: the kernels' conversion to u8 saturates for them (colour_of_lg1)
+    P.pal_u8 = (e->npal == 256 && (int)e->h_palette.size() == 256 && e->h_palette[P.ci_hi] == e->h_palette[255]) ? 1 : 0;
     P.db_precise = c.db_precise;
     P.pooled = e->pooled ? 1 : 0;
     P.R = e->R;
@@ -590,9 +602,11 @@ int launch_one(jade_engine* e, const KernelChoice& kc, KParams& P, cudaStream_t 
     static const long long run_min = [] { const char* v = getenv("JADE_RUN_MIN"); return v ? atoll(v) : 16ll; }(); // frames per warp that make a "long run"
     if (kc.fn_run && !no_run && P.hop == kc.run_hop && (P.fb == 1 ? P.bstride == P.hop : P.bstride == P.fb * P.hop) &&
         frames >= run_min * grid * kc.units_per_block)
-        fn = P.db ? kc.fn_run_db : kc.fn_run;
+        fn = P.db ? kc.fn_run_db : ((P.pal_u8 && kc.fn_run_u8) ? kc.fn_run_u8 : kc.fn_run);
+    else if (!P.db && P.pal_u8 && kc.fn_u8 && fn == kc.fn)
+        fn = kc.fn_u8;
     if (trace)
-        fprintf(stderr, "[jade] %s%s grid %d x %d threads, smem %d, blocks/SM %d, frames %lld\n", kc.name, (fn == kc.fn_run || fn == kc.fn_run_db) ? "+run" : "", grid,
+        fprintf(stderr, "[jade] %s%s grid %d x %d threads, smem %d, blocks/SM %d, frames %lld\n", kc.name, (fn == kc.fn_run || fn == kc.fn_run_db || fn == kc.fn_run_u8) ? "+run" : "", grid,
                 kc.threads, kc.smem, kc.blocks_per_sm, frames);
     if (P.ring_w > 0) {
         // streaming push: programmatic dependent launch behind ingest_kernel (every STFT kernel calls grid_dep_wait()

@@ -9,4 +9,6 @@ kernel_fn pk3_kernel(bool want_db, bool guard)
     if (guard) return want_db ? (kernel_fn)stft_pk3_kernel<true, PK3_GUARD> : (kernel_fn)stft_pk3_kernel<false, PK3_GUARD>;
     return want_db ? (kernel_fn)stft_pk3_kernel<true, PK3_STAGED> : (kernel_fn)stft_pk3_kernel<false, PK3_STAGED>;
 }
+// pixel-only, TMA-staged instantiation for palettes with P.pal_u8
+kernel_fn pk3_u8_kernel() { return (kernel_fn)jade::stft_pk3_kernel<false, jade::PK3_STAGED, true>; }
 } // namespace jade_k

@@ -16,4 +16,10 @@ kernel_fn pkz2048_run_kernel(bool want_db)
     using namespace jade;
     return want_db ? (kernel_fn)stft_pkz2048_kernel<true, PKZ_RING> : (kernel_fn)stft_pkz2048_kernel<false, PKZ_RING>;
 }
+// pixel-only instantiations for palettes with P.pal_u8 (run: the long-run instantiation)
+kernel_fn pkz2048_u8_kernel(bool run)
+{
+    using namespace jade;
+    return run ? (kernel_fn)stft_pkz2048_kernel<false, PKZ_RING, true> : (kernel_fn)stft_pkz2048_kernel<false, PKZ_ASYNC, true>;
+}
 } // namespace jade_k

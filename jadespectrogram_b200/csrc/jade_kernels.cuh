@@ -90,6 +90,7 @@ struct KParams {
     // lg >= clg_hi (dB >= m_Max) gives ci_hi = index of m_Max*0.9999
     float ck1, ck0, clg_hi;
     int ci_hi;
+    int pal_u8;             // 256 colours whose `>= m_Max` entry equals entry 255: the saturating float -> u8 conversion is the whole clamp (colour_of_lg1)
     int db_precise;         // 1: float(10.0*log10(double(p+1e-11f))) exactly as the reference; 0: MUFU log2
     // ---- rows
     int pooled;             // 0: rows are bins [k_lo,k_hi); 1: row r = max over bins [row_bins[r].lo, row_bins[r].hi)
@@ -164,6 +165,27 @@ JADE_DEVICE uint32_t colour_of_lg(float lg, const KParams& P, const uint32_t* pa
     return pal[idx];
 #endif
 }
+// The lookup of the packed N <= 2048 / N = 16384 kernels: their shared-memory table has npal + 1 entries, entry npal holding
+// the colour of CColorPalette's `value >= m_Max` rule (index ci_hi of 0.9999 m_Max, CColorpalette.h:34-35) --
+// lg ck1 + ck0 >= npal exactly when the dB value reaches m_Max -- so ONE integer clamp to [0, npal] does it (VIMNMX.RELU).
+// U8 (P.pal_u8: npal == 256 and entry 256 == entry 255, true for every 256-colour scheme with the reference's ranges): the
+// conversion itself saturates to [0, 255] (F2IP.U8.F32), no clamp instruction at all; same colours by construction.
+template <bool U8>
+JADE_DEVICE uint32_t colour_of_lg1(float lg, const KParams& P, const uint32_t* pal)
+{
+    const float x = fm(lg, P.ck1, P.ck0);
+    if (U8) {
+#if defined(JADE_EMU)
+        const int i = (int)x;
+        return pal[i < 0 ? 0 : (i > 255 ? 255 : i)];
+#else
+        unsigned idx;
+        asm("cvt.rzi.u8.f32 %0, %1;" : "=r"(idx) : "f"(x));
+        return pal[idx];
+#endif
+    }
+    return pal[max(min((int)x, P.npal), 0)];
+}
 // host side: fill ck1, ck0, clg_hi, ci_hi from pmin, pmax, pmaxc, pmult, npal
 inline void colour_fold(KParams& P)
 {
@@ -172,6 +194,20 @@ inline void colour_fold(KParams& P)
     P.clg_hi = P.pmax / 3.01029995663981195f;
     int ih = (int)((P.pmaxc > P.pmin ? P.pmaxc - P.pmin : 0.0f) * P.pmult);
     P.ci_hi = ih < 0 ? 0 : (ih > P.npal - 1 ? P.npal - 1 : ih);
+}
+
+// emit_bin with the one-clamp lookup (table of npal + 1 entries); EPS_IN: p already carries the + 1e-11 (seeded into the
+// power FMAs of a one-channel kernel)
+template <int MIXK, bool WANT_DB, bool U8, bool EPS_IN>
+JADE_DEVICE void emit_bin1(float p, float scale, uint32_t* pix, float* db, const KParams& P, const uint32_t* pal)
+{
+    const float lg = JADE_LOG2F(EPS_IN ? p : (MIXK == 1 /* MIX_SUM */ ? fm(p, scale, 1e-11f) : JADE_FADD(p, 1e-11f)));
+    if (WANT_DB) {
+        if (db) *db = JADE_FMUL(3.01029995663981195f, lg);
+        if (pix) *pix = colour_of_lg1<U8>(lg, P, pal);
+    } else {
+        *pix = colour_of_lg1<U8>(lg, P, pal);
+    }
 }
 
 // Fast-path epilogue of one bin (packed kernels): mixed power -> lg = log2(p' + 1e-11) -> dB value (optional) and pixel.

@@ -26,6 +26,7 @@
 // One warp transforms one frame: M = 1024 complex points z[m] = x[2m] + i x[2m+1], 32 per lane (m = s + 32 n1), radix-32
 // in registers, one transpose through shared memory, twisted radix-32 in registers: lane s ends with Z[s + 32 k2].
 #pragma once
+#include <type_traits>
 #include "jade_kernels.cuh"
 #include "jade_tmem.cuh"
 
@@ -480,7 +481,7 @@ struct PkCfgW {
     static constexpr int off_tw2 = off_win + (TM ? 0 : 32 * ROW * 8);
     static constexpr int off_twP = off_tw2 + (TM ? 0 : 32 * TROW * 8);
     static constexpr int off_pal = off_twP + (TM ? 0 : 32 * PROW * 8);
-    static JADE_HD int off_bar(int npal) { return off_pal + (npal * 4 + 15) / 16 * 16; } // one mbarrier per warp (+ the tensor-memory address)
+    static JADE_HD int off_bar(int npal) { return off_pal + ((npal + 1) * 4 + 15) / 16 * 16; } // palette + its `>= m_Max` entry (colour_of_lg1); then one mbarrier per warp (+ the tensor-memory address)
     static JADE_HD int off_xch(int npal) { return off_bar(npal) + (WARPS * 8 + 8 + 15) / 16 * 16; }
     static JADE_HD int smem_bytes(int npal) { return off_xch(npal) + WARPS * XCH * 8; }
 };
@@ -629,7 +630,7 @@ JADE_KERNEL(PkCfgFor<MIXK>::WARPS * 32, JADE_PK_CTAS) stft_pk2048_kernel(const K
             s_twP[s * Cfg::PROW + q] = pk(w.y, -w.x);
         }
     }
-    for (int i = threadIdx.x; i < P.npal; i += blockDim.x) s_pal[i] = P.palette[i];
+    for (int i = threadIdx.x; i <= P.npal; i += blockDim.x) s_pal[i] = P.palette[i < P.npal ? i : P.ci_hi];
     __syncthreads();
     if constexpr (Cfg::TM) tm_fence_after_sync();
     grid_dep_wait();
@@ -654,7 +655,10 @@ JADE_KERNEL(PkCfgFor<MIXK>::WARPS * 32, JADE_PK_CTAS) stft_pk2048_kernel(const K
 
     // One bin: dB, palette, packed pixel (and the dB value for the streaming ring).  Reference orientation: bin k lands
     // in row M - k, so lane s writes rows M-s-32q (bins s+32q) and rows s+32q (bins M-s-32q): both coalesced.
-    auto emit = [&](float p, uint32_t* pix, float* db) { emit_bin<MIXK, WANT_DB>(p, scale, pix, db, P, s_pal); };
+    // (one contributing channel: the + 1e-11 is seeded into the power FMAs)
+    auto emit = [&](auto u8, float p, uint32_t* pix, float* db) {
+        emit_bin1<MIXK, WANT_DB, decltype(u8)::value, MIXK == MIX_NONE>(p, scale, pix, db, P, s_pal);
+    };
 
     // frames of this warp: dealt round-robin (g, g + gstep, ...), or -- PK_LD_RING* -- one contiguous run
     unsigned g = blockIdx.x * Cfg::WARPS + warp, g_end = total, g_inc = gstep;
@@ -855,27 +859,32 @@ JADE_KERNEL(PkCfgFor<MIXK>::WARPS * 32, JADE_PK_CTAS) stft_pk2048_kernel(const K
                 const float a = lo(u[16]), b = hi(u[16]); // bin 512 (lane 0, self-paired): X = 2 conj Z
                 amid = fm(JADE_FMUL(4.0f, a), a, fm(JADE_FMUL(4.0f, b), b, amid));
             } else {
-                uint32_t* p_lo = o.pix ? o.pix + (M - s) : nullptr;
-                uint32_t* p_hi = o.pix ? o.pix + s : nullptr;
-                float* d_lo = (WANT_DB && o.db) ? o.db + s : nullptr;
-                float* d_hi = (WANT_DB && o.db) ? o.db + (M - s) : nullptr;
+                // (two copies behind a launch-uniform branch: with the u8 palette the float -> integer conversion is the clamp)
+                auto finish = [&](auto u8) {
+                    uint32_t* p_lo = o.pix ? o.pix + (M - s) : nullptr;
+                    uint32_t* p_hi = o.pix ? o.pix + s : nullptr;
+                    float* d_lo = (WANT_DB && o.db) ? o.db + s : nullptr;
+                    float* d_hi = (WANT_DB && o.db) ? o.db + (M - s) : nullptr;
 #pragma unroll
-                for (int q = 0; q < 16; ++q) {
-                    const f2 zp = sel2(s == 0, u[(32 - q) & 31], shfl2(u[31 - q], partner));
-                    const f2 A = add2(u[q], conj2(zp));
-                    const f2 Bv = sub2(u[q], conj2(zp));
-                    const f2 T = cmul2(Bv, split_tw(q));
-                    const f2 xp = add2(A, T), xm = sub2(A, T);
-                    const float pl = fm(lo(xp), lo(xp), fm(hi(xp), hi(xp), MIXK == MIX_NONE ? 0.f : alo[q]));
-                    const float ph = fm(lo(xm), lo(xm), fm(hi(xm), hi(xm), MIXK == MIX_NONE ? 0.f : ahi[q]));
-                    emit(pl, p_lo ? p_lo - 32 * q : nullptr, d_lo ? d_lo + 32 * q : nullptr);
-                    emit(ph, p_hi ? p_hi + 32 * q : nullptr, d_hi ? d_hi - 32 * q : nullptr);
-                }
-                if (s == 0) {
-                    const float a = lo(u[16]), b = hi(u[16]);
-                    const float pm = fm(JADE_FMUL(4.0f, a), a, fm(JADE_FMUL(4.0f, b), b, MIXK == MIX_NONE ? 0.f : amid));
-                    emit(pm, o.pix ? o.pix + 512 : nullptr, (WANT_DB && o.db) ? o.db + 512 : nullptr);
-                }
+                    for (int q = 0; q < 16; ++q) {
+                        const f2 zp = sel2(s == 0, u[(32 - q) & 31], shfl2(u[31 - q], partner));
+                        const f2 A = add2(u[q], conj2(zp));
+                        const f2 Bv = sub2(u[q], conj2(zp));
+                        const f2 T = cmul2(Bv, split_tw(q));
+                        const f2 xp = add2(A, T), xm = sub2(A, T);
+                        const float pl = fm(lo(xp), lo(xp), fm(hi(xp), hi(xp), MIXK == MIX_NONE ? 1e-11f : alo[q]));
+                        const float ph = fm(lo(xm), lo(xm), fm(hi(xm), hi(xm), MIXK == MIX_NONE ? 1e-11f : ahi[q]));
+                        emit(u8, pl, p_lo ? p_lo - 32 * q : nullptr, d_lo ? d_lo + 32 * q : nullptr);
+                        emit(u8, ph, p_hi ? p_hi + 32 * q : nullptr, d_hi ? d_hi - 32 * q : nullptr);
+                    }
+                    if (s == 0) {
+                        const float a = lo(u[16]), b = hi(u[16]);
+                        const float pm = fm(JADE_FMUL(4.0f, a), a, fm(JADE_FMUL(4.0f, b), b, MIXK == MIX_NONE ? 1e-11f : amid));
+                        emit(u8, pm, o.pix ? o.pix + 512 : nullptr, (WANT_DB && o.db) ? o.db + 512 : nullptr);
+                    }
+                };
+                if (P.pal_u8) finish(std::true_type{});
+                else finish(std::false_type{});
             }
         }
     }
@@ -908,7 +917,7 @@ struct PkPairCfg {
     static constexpr int off_tw2 = off_win + 32 * PkCfg::ROW * 8;
     static constexpr int off_twP = off_tw2 + 32 * PkCfg::TROW * 8;
     static constexpr int off_pal = off_twP + 32 * PkCfg::PROW * 8;
-    static JADE_HD int off_bar(int npal) { return off_pal + (npal * 4 + 15) / 16 * 16; }
+    static JADE_HD int off_bar(int npal) { return off_pal + ((npal + 1) * 4 + 15) / 16 * 16; }
     static JADE_HD int off_xch(int npal) { return off_bar(npal) + (WARPS * 8 + 15) / 16 * 16; }
     static JADE_HD int smem_bytes(int npal) { return off_xch(npal) + WARPS * 2 * PkCfg::XCH * 8; }
 };
@@ -939,7 +948,7 @@ JADE_KERNEL(PkPairCfg::WARPS * 32, 1) stft_pk2048x2_kernel(const KParams P)
         const cpx w = P.twP[s + 32 * q];
         s_twP[s * Cfg::PROW + q] = pk(w.y, -w.x);
     }
-    for (int i = threadIdx.x; i < P.npal; i += blockDim.x) s_pal[i] = P.palette[i];
+    for (int i = threadIdx.x; i <= P.npal; i += blockDim.x) s_pal[i] = P.palette[i < P.npal ? i : P.ci_hi];
     __syncthreads();
     grid_dep_wait();
 
@@ -964,7 +973,7 @@ JADE_KERNEL(PkPairCfg::WARPS * 32, 1) stft_pk2048x2_kernel(const KParams P)
         __syncwarp();
 #endif
     };
-    auto emit = [&](float p, uint32_t* pix, float* db) { emit_bin<MIX_SUM, WANT_DB>(p, scale, pix, db, P, s_pal); };
+    auto emit = [&](float p, uint32_t* pix, float* db) { emit_bin1<MIX_SUM, WANT_DB, false, false>(p, scale, pix, db, P, s_pal); };
 
     unsigned g = blockIdx.x * WARPS + warp;
     if (g < total) stage(g);

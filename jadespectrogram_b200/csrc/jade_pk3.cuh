@@ -109,7 +109,8 @@ enum { PK3_STAGED = 0, PK3_GUARD = 1 };
 // PK3_GUARD: boundary frames / unaligned geometries, the thread fills its own column with bounds-checked loads first.  The
 // arithmetic is the same, so streaming, batch and sharded renderings agree bit for bit.  (One instantiation that decides per
 // frame is 7 % slower on interior frames -- registers -- than the pair, profiles/r02c_pk3_variants.txt.)
-template <bool WANT_DB, int LD>
+// U8: instantiation for P.pal_u8 palettes (colour_of_lg1), picked by launch_one for the pixel-only launches
+template <bool WANT_DB, int LD, bool U8 = false>
 JADE_KERNEL(Pk3Cfg::THREADS, 2) stft_pk3_kernel(const KParams P)
 {
     using Cfg = Pk3Cfg;
@@ -330,8 +331,8 @@ JADE_KERNEL(Pk3Cfg::THREADS, 2) stft_pk3_kernel(const KParams P)
                 const float plo = fm(lo(xp), lo(xp), fm(hi(xp), hi(xp), 1e-11f));
                 const float phi = fm(lo(xm), lo(xm), fm(hi(xm), hi(xm), 1e-11f));
                 const int k = kb + 512 * q;
-                pkz_emit<WANT_DB>(plo, o.pix ? o.pix + (M - k) : nullptr, (WANT_DB && o.db) ? o.db + k : nullptr, P, s_pal); // bin k -> row M - k
-                pkz_emit<WANT_DB>(phi, o.pix ? o.pix + k : nullptr, (WANT_DB && o.db) ? o.db + (M - k) : nullptr, P, s_pal);
+                pkz_emit<WANT_DB, U8>(plo, o.pix ? o.pix + (M - k) : nullptr, (WANT_DB && o.db) ? o.db + k : nullptr, P, s_pal); // bin k -> row M - k
+                pkz_emit<WANT_DB, U8>(phi, o.pix ? o.pix + k : nullptr, (WANT_DB && o.db) ? o.db + (M - k) : nullptr, P, s_pal);
             }
         };
         if (warp == 4) split_emit(std::true_type{});
@@ -339,7 +340,7 @@ JADE_KERNEL(Pk3Cfg::THREADS, 2) stft_pk3_kernel(const KParams P)
         if (L3.self) { // bin M/2 (self-paired, A[8] of that lane): X = 2 conj Z
             const float a = lo(ua[8]), b = hi(ua[8]);
             const float p = fm(JADE_FMUL(4.0f, a), a, fm(JADE_FMUL(4.0f, b), b, 1e-11f));
-            pkz_emit<WANT_DB>(p, o.pix ? o.pix + M / 2 : nullptr, (WANT_DB && o.db) ? o.db + M / 2 : nullptr, P, s_pal);
+            pkz_emit<WANT_DB, U8>(p, o.pix ? o.pix + M / 2 : nullptr, (WANT_DB && o.db) ? o.db + M / 2 : nullptr, P, s_pal);
         }
     }
     tm_fence_before_sync();

@@ -18,6 +18,7 @@
 //   epilogue as in jade_pk.cuh.
 // Same reference lines replaced as jade_kernels.cuh (Spectrogram.cpp:50-56,137-145,64-107,634-647; CColorpalette.h:32-47).
 #pragma once
+#include <type_traits>
 #include "jade_pk.cuh"
 #include "jade_tmem.cuh"
 
@@ -99,7 +100,7 @@ struct PkSmallCfg {
     static constexpr int off_twI = off_win + (TM ? 0 : T * ROW * 8);
     static constexpr int off_twP = off_twI + (TM ? 0 : T * ROW * 8);
     static constexpr int off_pal = off_twP + (TM ? 0 : T * PROW * 8);
-    static JADE_HD int off_bar(int npal) { return off_pal + (npal * 4 + 15) / 16 * 16; } // one mbarrier per warp (+ the tensor-memory address)
+    static JADE_HD int off_bar(int npal) { return off_pal + ((npal + 1) * 4 + 15) / 16 * 16; } // palette + its `>= m_Max` entry (colour_of_lg1); then one mbarrier per warp (+ the tensor-memory address)
     static JADE_HD int off_xch(int npal) { return off_bar(npal) + (WARPS * 8 + 8 + 15) / 16 * 16; }
     static JADE_HD int smem_bytes(int npal) { return off_xch(npal) + WARPS * F * FS * 8; }
 };
@@ -194,7 +195,7 @@ JADE_KERNEL((PkSmallCfg<T, MIXK == MIX_NONE>::WARPS * 32), (PkSmallCfg<T, MIXK =
         s_twP[s * Cfg::PROW + q] = pk(w.y, -w.x);
     }
     }
-    for (int i = threadIdx.x; i < P.npal; i += blockDim.x) s_pal[i] = P.palette[i];
+    for (int i = threadIdx.x; i <= P.npal; i += blockDim.x) s_pal[i] = P.palette[i < P.npal ? i : P.ci_hi];
     __syncthreads();
     if constexpr (Cfg::TM) tm_fence_after_sync();
     grid_dep_wait();
@@ -253,9 +254,10 @@ JADE_KERNEL((PkSmallCfg<T, MIXK == MIX_NONE>::WARPS * 32), (PkSmallCfg<T, MIXK =
         bool active;
         frame_of(g, stream, j, st, active);
 
-        float alo[16], ahi[16], amid = 0.f; // bins k(q) = s + T i + 32 k2 / M - k(q) / M/2 (lane s = 0)
+        constexpr float seed = MIXK == MIX_NONE ? 1e-11f : 0.f; // one contributing channel: the + 1e-11 (Spectrogram.cpp:36) rides on the power FMAs
+        float alo[16], ahi[16], amid = seed; // bins k(q) = s + T i + 32 k2 / M - k(q) / M/2 (lane s = 0)
 #pragma unroll
-        for (int q = 0; q < 16; ++q) alo[q] = ahi[q] = 0.f;
+        for (int q = 0; q < 16; ++q) alo[q] = ahi[q] = seed;
 
         for (int ch = ch0; ch < ch1; ++ch) {
             const float* x = P.samples + stream * P.stream_stride + ch * P.channel_stride;
@@ -376,13 +378,19 @@ JADE_KERNEL((PkSmallCfg<T, MIXK == MIX_NONE>::WARPS * 32), (PkSmallCfg<T, MIXK =
         uint32_t* p_hi = o.pix ? o.pix + s : nullptr;       // bin M-k(q) -> row k(q)
         float* d_lo = (WANT_DB && o.db) ? o.db + s : nullptr;
         float* d_hi = (WANT_DB && o.db) ? o.db + (M - s) : nullptr;
+        // (two copies behind a launch-uniform branch: with the u8 palette the float -> integer conversion is the clamp)
+        auto finish = [&](auto u8) {
+            constexpr bool U8 = decltype(u8)::value;
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-            const int koff = T * (q / H) + 32 * (q % H); // k(q) - s
-            emit_bin<MIXK, WANT_DB>(alo[q], scale, (!WANT_DB || p_lo) ? p_lo - koff : nullptr, d_lo ? d_lo + koff : nullptr, P, s_pal);
-            emit_bin<MIXK, WANT_DB>(ahi[q], scale, (!WANT_DB || p_hi) ? p_hi + koff : nullptr, d_hi ? d_hi - koff : nullptr, P, s_pal);
-        }
-        if (s == 0) emit_bin<MIXK, WANT_DB>(amid, scale, (!WANT_DB || o.pix) ? o.pix + M / 2 : nullptr, (WANT_DB && o.db) ? o.db + M / 2 : nullptr, P, s_pal);
+            for (int q = 0; q < 16; ++q) {
+                const int koff = T * (q / H) + 32 * (q % H); // k(q) - s
+                emit_bin1<MIXK, WANT_DB, U8, MIXK == MIX_NONE>(alo[q], scale, (!WANT_DB || p_lo) ? p_lo - koff : nullptr, d_lo ? d_lo + koff : nullptr, P, s_pal);
+                emit_bin1<MIXK, WANT_DB, U8, MIXK == MIX_NONE>(ahi[q], scale, (!WANT_DB || p_hi) ? p_hi + koff : nullptr, d_hi ? d_hi - koff : nullptr, P, s_pal);
+            }
+            if (s == 0) emit_bin1<MIXK, WANT_DB, U8, MIXK == MIX_NONE>(amid, scale, (!WANT_DB || o.pix) ? o.pix + M / 2 : nullptr, (WANT_DB && o.db) ? o.db + M / 2 : nullptr, P, s_pal);
+        };
+        if (P.pal_u8) finish(std::true_type{});
+        else finish(std::false_type{});
     }
     if constexpr (Cfg::TM) {
         tm_fence_before_sync();

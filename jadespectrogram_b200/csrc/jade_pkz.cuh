@@ -139,17 +139,10 @@ enum { PKZ_ASYNC = 0, PKZ_GUARD = 1, PKZ_RING = 2 };
 // (optional) = 3.0103 lg; palette index = trunc(lg ck1 + ck0) clamped to [0, npal] by ONE integer min/max, where entry
 // npal of the shared-memory table holds the colour of CColorPalette's `value >= m_Max` rule (index of 0.9999 m_Max,
 // CColorpalette.h:34-35): lg ck1 + ck0 >= npal exactly when the dB value reaches m_Max.
-template <bool WANT_DB>
+template <bool WANT_DB, bool U8 = false>
 JADE_DEVICE void pkz_emit(float p, uint32_t* pix, float* db, const KParams& P, const uint32_t* pal)
 {
-    const float lg = JADE_LOG2F(p);
-    const uint32_t c = pal[max(min((int)fm(lg, P.ck1, P.ck0), P.npal), 0)];
-    if (WANT_DB) {
-        if (db) *db = JADE_FMUL(3.01029995663981195f, lg);
-        if (pix) *pix = c;
-    } else {
-        *pix = c;
-    }
+    emit_bin1<MIX_NONE, WANT_DB, U8, true>(p, 1.0f, pix, db, P, pal);
 }
 
 // (stream, column) walked incrementally: g -> g + gstep without a division per frame
@@ -174,7 +167,10 @@ struct PkzWalk {
     }
 };
 
-template <bool WANT_DB, int LD>
+// U8: instantiation for P.pal_u8 palettes (colour_of_lg1: the float -> u8 conversion is the clamp; identical colours), picked by
+// launch_one for the pixel-only launches -- a launch-uniform branch around two epilogue copies costs registers this kernel
+// does not have (-1.5 %, gpurun_out/ab8.txt)
+template <bool WANT_DB, int LD, bool U8 = false>
 JADE_KERNEL(PkzCfg::WARPS * 32, 1) stft_pkz2048_kernel(const KParams P)
 {
     using Cfg = PkzCfg;
@@ -470,10 +466,10 @@ JADE_KERNEL(PkzCfg::WARPS * 32, 1) stft_pkz2048_kernel(const KParams P)
             float* d_b = (WANT_DB && o.db) ? o.db + kb : nullptr;
 #pragma unroll
             for (int q = 0; q < 16; ++q) {
-                pkz_emit<WANT_DB>(oa[q], (!WANT_DB || p_a) ? p_a - 64 * q : nullptr, d_a ? d_a + 64 * q : nullptr, P, s_pal);
-                pkz_emit<WANT_DB>(ob[q], (!WANT_DB || p_b) ? p_b - 64 * q : nullptr, d_b ? d_b + 64 * q : nullptr, P, s_pal);
+                pkz_emit<WANT_DB, U8>(oa[q], (!WANT_DB || p_a) ? p_a - 64 * q : nullptr, d_a ? d_a + 64 * q : nullptr, P, s_pal);
+                pkz_emit<WANT_DB, U8>(ob[q], (!WANT_DB || p_b) ? p_b - 64 * q : nullptr, d_b ? d_b + 64 * q : nullptr, P, s_pal);
             }
-            if (s == 0) pkz_emit<WANT_DB>(omid, (!WANT_DB || o.pix) ? o.pix : nullptr, (WANT_DB && o.db) ? o.db + 1024 : nullptr, P, s_pal);
+            if (s == 0) pkz_emit<WANT_DB, U8>(omid, (!WANT_DB || o.pix) ? o.pix : nullptr, (WANT_DB && o.db) ? o.db + 1024 : nullptr, P, s_pal);
         }
         cur = nxt;
     }
