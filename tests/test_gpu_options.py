@@ -68,7 +68,9 @@ def test_cfg5_geometry_log_rows_n65536(gpu_engine_factory):
 
 @pytest.mark.parametrize("scheme,n,invert,rng", [("viridis", 256, False, (-80.0, 0.0)), ("rainbow", 64, True, (-100.0, -10.0)),
                                                  ("hot", 1024, False, (20.0, -60.0)), ("bw", 2, False, (-30.0, -30.0 + 1e-3)),
-                                                 ("mono", 7, False, (-50.0, 50.0)), ("plasma", 255, True, (-120.0, 60.0))])
+                                                 ("mono", 7, False, (-50.0, 50.0)), ("plasma", 255, True, (-120.0, 60.0)),
+                                                 # 256 colours, `>= m_Max` entry != entry 255 (index of 0.9999 * 59 is 254): not a u8 palette
+                                                 ("rainbow", 256, False, (58.0, 59.0))])
 def test_palettes_and_ranges(gpu_engine_factory, scheme, n, invert, rng):
     N, hop = 1024, 256
     x = signals.streams(1, 2, hop * 16, FS)
@@ -87,6 +89,25 @@ def test_palettes_and_ranges(gpu_engine_factory, scheme, n, invert, rng):
     ref = _ref_pixels(odb, scheme, n, rng[0], rng[1], invert)[:, ::-1]
     parity.check_pixels(pix[0], ref, odb[:, ::-1], min(rng), max(rng), n)
     assert eng.lookup_color(odb[3, 40]) == int(ref[3, N // 2 - 40] & 0xFFFFFF)
+    pix2, _ = eng.render_batch(x)  # the pixel-only instantiation
+    assert np.array_equal(pix2, pix)
+
+
+@pytest.mark.parametrize("N,hop,ch", [(2048, 512, 2), (16384, 4096, 1), (2048, 256, 1), (1024, 512, 1)])
+def test_u8_palette_kernels_match_the_clamping_ones(gpu_engine_factory, N, hop, ch):
+    """256-colour palettes whose `>= m_Max` colour is the last one take kernels in which the saturating float -> u8 conversion
+    is the whole index clamp (KParams::pal_u8; separate pixel-only instantiations for N = 2048 stereo and N = 16384): same
+    pixels as the instantiations with the integer clamp (the dB-storing ones) and, for another range, as the oracle."""
+    x = signals.streams(2, ch, hop * 40 + N, FS)
+    x *= 30.0
+    eng = gpu_engine_factory(sample_rate=FS, fft_size=N, hop=hop, channels=ch)
+    for rng in ((-50.0, 50.0), (0.0, 60.0), (58.0, 59.0)):
+        eng.set_value_range(*rng)
+        pix_db, db = eng.render_batch(x, want_db=True)
+        pix, _ = eng.render_batch(x)
+        assert np.array_equal(pix, pix_db), rng
+    odb, _ = O.render_batch(x[1], fft_size=N, hop=hop, ncols=pix.shape[1])
+    parity.check_pixels(pix[1], _ref_pixels(odb, "jade", 256, 58.0, 59.0)[:, ::-1], odb[:, ::-1], 58.0, 59.0, 256)
 
 
 def test_rgba8_byte_order(gpu_engine_factory):
