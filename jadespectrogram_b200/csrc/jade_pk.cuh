@@ -690,14 +690,34 @@ JADE_KERNEL(PkCfgFor<MIXK>::WARPS * 32, JADE_PK_CTAS) stft_pk2048_kernel(const K
         __syncwarp();
 #endif
     };
+    // PK_LD_RING* (evenly spaced columns one hop = 64 CH samples apart, by dispatch): the walk is (stream, column) plus one source
+    // and one output pointer, advanced by one addition per frame -- no division by the column count and no 64-bit multiplies
+    // per frame (~100 of 1200 instructions)
+    unsigned r_stream = 0, r_col = 0;
+    const float* r_x = nullptr;
+    ColOut r_o{nullptr, nullptr};
     if (STAGED && g < g_end) {
         const PkUnit un = pk_unit(P, g);
-        pk_prefetch(xw, P.samples + un.stream * P.stream_stride + ch0 * P.channel_stride + un.st, s, bar);
+        r_stream = (unsigned)un.stream;
+        r_col = (unsigned)(un.j - P.first_col);
+        r_x = P.samples + un.stream * P.stream_stride + ch0 * P.channel_stride + un.st;
+        r_o = col_out(P, un.stream, un.j);
+        if (!WANT_DB) r_o.db = nullptr;
+        pk_prefetch(xw, r_x, s, bar);
     }
     for (; g < g_end; g += g_inc) {
-        const PkUnit un = pk_unit(P, g);
-        const ColOut o = col_out(P, un.stream, un.j);
-        const float* x = P.samples + un.stream * P.stream_stride + ch0 * P.channel_stride + un.st; // frame, channel ch
+        PkUnit un;
+        ColOut o;
+        const float* x; // frame, channel ch
+        if constexpr (RING) {
+            un.stream = (int)r_stream, un.j = 0, un.st = 0; // (un.j / un.st: guarded loads only)
+            o = r_o;
+            x = r_x;
+        } else {
+            un = pk_unit(P, g);
+            o = col_out(P, un.stream, un.j);
+            x = P.samples + un.stream * P.stream_stride + ch0 * P.channel_stride + un.st;
+        }
 
         float alo[16], ahi[16], amid = 0.f; // power of bins s+32q / M-(s+32q) / 512 (lane 0) of the channels so far
 #pragma unroll
@@ -806,15 +826,21 @@ JADE_KERNEL(PkCfgFor<MIXK>::WARPS * 32, JADE_PK_CTAS) stft_pk2048_kernel(const K
                 if (!last) {
                     pk_prefetch(xw, x + P.channel_stride, s, bar);
                 } else if (g + g_inc < g_end) {
-                    const PkUnit nx = pk_unit(P, g + g_inc);
-                    const float* nsrc = P.samples + nx.stream * P.stream_stride + ch0 * P.channel_stride + nx.st;
-                    if (RING) {
+                    if constexpr (RING) {
                         // the next frame continues this one (same stream, one hop further): only its last chunk is new
-                        warm = nx.stream == un.stream && nx.st == un.st + 64 * CH;
-                        if (warm) prefetch_last(nsrc);
-                        else pk_prefetch(xw, nsrc, s, bar);
+                        warm = ++r_col != (unsigned)P.ncols;
+                        if (warm) {
+                            r_x += 64 * CH;
+                            prefetch_last(r_x);
+                        } else {
+                            r_col = 0;
+                            ++r_stream;
+                            r_x = P.samples + (long long)r_stream * P.stream_stride + ch0 * P.channel_stride + frame_start(P, P.first_col);
+                            pk_prefetch(xw, r_x, s, bar);
+                        }
                     } else {
-                        pk_prefetch(xw, nsrc, s, bar);
+                        const PkUnit nx = pk_unit(P, g + g_inc);
+                        pk_prefetch(xw, P.samples + nx.stream * P.stream_stride + ch0 * P.channel_stride + nx.st, s, bar);
                     }
                 }
             }
@@ -885,6 +911,17 @@ JADE_KERNEL(PkCfgFor<MIXK>::WARPS * 32, JADE_PK_CTAS) stft_pk2048_kernel(const K
                 };
                 if (P.pal_u8) finish(std::true_type{});
                 else finish(std::false_type{});
+            }
+        }
+        if constexpr (RING) {
+            if (g + g_inc < g_end) { // output column of the next frame
+                if (warm && P.ring_w == 0) {
+                    if (r_o.pix) r_o.pix += P.R;
+                    if (r_o.db) r_o.db += P.B;
+                } else {
+                    r_o = col_out(P, (int)r_stream, P.first_col + r_col);
+                    if (!WANT_DB) r_o.db = nullptr;
+                }
             }
         }
     }
