@@ -220,39 +220,57 @@ JADE_KERNEL((PkSmallCfg<T, MIXK == MIX_NONE>::WARPS * 32), (PkSmallCfg<T, MIXK =
     unsigned long long* bar = s_bar + warp;
     unsigned copies = 0; // staged groups of this warp waited for so far (mbarrier phase parity)
 
-    // frame of this lane in group gg: stream, column (clamped to the last one), first sample
-    auto frame_of = [&](unsigned gg, int& stream_, long long& j_, long long& st_, bool& active_) {
-        stream_ = (int)(gg / groups);
-        int jrel = (int)(gg - (unsigned)stream_ * groups) * F + f;
+    // frame of this lane in group grp of a stream: column (clamped to the last one), first sample
+    auto frame_of = [&](unsigned grp, long long& j_, long long& st_, bool& active_) {
+        int jrel = (int)grp * F + f;
         active_ = jrel < P.ncols;
         if (!active_) jrel = P.ncols - 1; // transform the last column again, store nothing
         j_ = P.first_col + jrel;
         st_ = frame_start(P, j_);
     };
+    // the warp's groups g, g + gstep, ... as (stream, group in the stream), advanced without a division per group
+    const unsigned w_dq = gstep / groups, w_dr = gstep - w_dq * groups;
+    // (T >= 8; the 128-register instantiations for N <= 256 lose 2..3 % to the two more live registers and keep the division)
+    constexpr bool WALK = T >= 8;
+    auto advance = [&](unsigned& stream_, unsigned& grp_) {
+        stream_ += w_dq;
+        grp_ += w_dr;
+        if (grp_ >= groups) {
+            grp_ -= groups;
+            ++stream_;
+        }
+    };
     // GUARD = false: interior frames starting on a multiple of 4 samples with 16-byte aligned channel bases
     // (P.aligned4).  The TMA engine copies the F frames (8 KB together) a warp transforms next -- channel ch of group gg --
     // into the warp's F tiles while the warp is still busy with the split and the epilogue of the previous ones: lane 0
     // announces the bytes on the warp's mbarrier, then the first lane of every frame issues its cp.async.bulk.
-    auto stage = [&](unsigned gg, int ch) {
-        int stream_;
+    auto stage = [&](unsigned stream_, unsigned grp_, int ch) {
         long long j_, st_;
         bool act_;
-        frame_of(gg, stream_, j_, st_, act_);
+        frame_of(grp_, j_, st_, act_);
         if (lane == 0) mbar_expect_tx(bar, F * M * 8);
         __syncwarp();
-        if (s == 0) bulk_copy_issue(xw, P.samples + stream_ * P.stream_stride + ch * P.channel_stride + st_, M * 8, bar);
+        if (s == 0) bulk_copy_issue(xw, P.samples + (long long)stream_ * P.stream_stride + ch * P.channel_stride + st_, M * 8, bar);
 #if defined(JADE_EMU)
         __syncwarp();
 #endif
     };
 
     unsigned g = blockIdx.x * Cfg::WARPS + warp;
-    if (!GUARD && g < total) stage(g, ch0);
-    for (; g < total; g += gstep) {
-        int stream;
+    unsigned w_stream = g / groups, w_grp = g - w_stream * groups;
+    unsigned n_stream = w_stream, n_grp = w_grp; // the warp's next group
+    if (!GUARD && g < total) stage(w_stream, w_grp, ch0);
+    for (; g < total; g += gstep, w_stream = n_stream, w_grp = n_grp) {
+        if constexpr (WALK) {
+            advance(n_stream, n_grp);
+        } else {
+            w_stream = g / groups;
+            w_grp = g - w_stream * groups;
+        }
+        const int stream = (int)w_stream;
         long long j, st;
         bool active;
-        frame_of(g, stream, j, st, active);
+        frame_of(w_grp, j, st, active);
 
         constexpr float seed = MIXK == MIX_NONE ? 1e-11f : 0.f; // one contributing channel: the + 1e-11 (Spectrogram.cpp:36) rides on the power FMAs
         float alo[16], ahi[16], amid = seed; // bins k(q) = s + T i + 32 k2 / M - k(q) / M/2 (lane s = 0)
@@ -334,8 +352,15 @@ JADE_KERNEL((PkSmallCfg<T, MIXK == MIX_NONE>::WARPS * 32), (PkSmallCfg<T, MIXK =
             }
             __syncwarp(); // the tiles are free again
             if (!GUARD) { // stage what this warp transforms next: the next channel of this group, or its next group
-                if (ch + 1 < ch1) stage(g, ch + 1);
-                else if (g + gstep < total) stage(g + gstep, ch0);
+                if (ch + 1 < ch1) stage(w_stream, w_grp, ch + 1);
+                else if (g + gstep < total) {
+                    if constexpr (WALK) {
+                        stage(n_stream, n_grp, ch0);
+                    } else {
+                        const unsigned gn = g + gstep, sn = gn / groups;
+                        stage(sn, gn - sn * groups, ch0);
+                    }
+                }
             }
             // Pair split.  Z[M - k] of pair q = i H + k2 (k = s + T i + 32 k2) is register (F-1-i) T + (T-1-k2) of lane
             // T - s of the same frame and arrives by SHFL.IDX; lane s = 0 pairs with its own lane0_partner<T>(q).
