@@ -147,22 +147,30 @@ JADE_DEVICE void pkz_emit(float p, uint32_t* pix, float* db, const KParams& P, c
 
 // (stream, column) walked incrementally: g -> g + gstep without a division per frame
 struct PkzWalk {
-    unsigned stream, col, dq, dr, ncols;
+    unsigned stream, col, dq, dr;
+    template <bool UNIT> // UNIT: gstep == 1 (a contiguous run): no quotient / remainder to carry
     JADE_DEVICE void init(unsigned g, unsigned gstep, unsigned nc)
     {
-        ncols = nc;
         stream = g / nc;
         col = g - stream * nc;
-        dq = gstep / nc;
-        dr = gstep - dq * nc;
+        dq = UNIT ? 0u : gstep / nc;
+        dr = UNIT ? 1u : gstep - dq * nc;
     }
-    JADE_DEVICE void next()
+    template <bool UNIT>
+    JADE_DEVICE void next(unsigned nc)
     {
-        stream += dq;
-        col += dr;
-        if (col >= ncols) {
-            col -= ncols;
-            ++stream;
+        if (UNIT) {
+            if (++col == nc) {
+                col = 0;
+                ++stream;
+            }
+        } else {
+            stream += dq;
+            col += dr;
+            if (col >= nc) {
+                col -= nc;
+                ++stream;
+            }
         }
     }
 };
@@ -260,10 +268,10 @@ JADE_KERNEL(PkzCfg::WARPS * 32, 1) stft_pkz2048_kernel(const KParams P)
         const unsigned per = (total + gstep - 1) / gstep;
         const unsigned b = min(total, g * per), e = min(total, b + per);
         my_iters = e - b;
-        cur.init(b < total ? b : 0u, 1u, (unsigned)P.ncols);
+        cur.template init<true>(b < total ? b : 0u, 1u, (unsigned)P.ncols);
     } else {
         my_iters = g < total ? (total - g + gstep - 1) / gstep : 0;
-        cur.init(g < total ? g : 0u, gstep, (unsigned)P.ncols);
+        cur.template init<false>(g < total ? g : 0u, gstep, (unsigned)P.ncols);
     }
     nxt = cur;
 
@@ -411,10 +419,11 @@ JADE_KERNEL(PkzCfg::WARPS * 32, 1) stft_pkz2048_kernel(const KParams P)
         __syncwarp(); // the buffer is free again
         const bool more = it + 1 < my_iters;
         if (more) {
-            nxt.next();
+            nxt.template next<RING>((unsigned)P.ncols);
             if constexpr (RING) {
                 // the next frame continues this one (same stream, one chunk further): three of its chunks are in the ring already
-                warm = nxt.col != 0 && frame_start(P, P.first_col + nxt.col) == frame_start(P, P.first_col + cur.col) + Cfg::N / 4;
+                // (evenly spaced columns N/4 apart by dispatch, launch_one: the next column of the same stream is one chunk on)
+                warm = nxt.col != 0;
                 stage(nxt, warm);
             } else if (STAGED) {
                 stage(nxt);
