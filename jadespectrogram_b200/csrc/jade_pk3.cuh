@@ -182,18 +182,26 @@ JADE_KERNEL(Pk3Cfg::THREADS, 2) stft_pk3_kernel(const KParams P)
     const unsigned total = (unsigned)P.ncols * (unsigned)P.nstreams;
     int ch0, ch1;
     channel_range(P, ch0, ch1);
-    auto frame_of = [&](unsigned gg, int& stream_, long long& j_, long long& st_, bool& staged_) {
-        stream_ = (int)(gg / (unsigned)P.ncols);
-        j_ = P.first_col + (gg - (unsigned)stream_ * (unsigned)P.ncols);
+    // the CTA's frames g, g + gridDim.x, ... as (stream, column), advanced without a division per frame
+    const unsigned w_dq = gridDim.x / (unsigned)P.ncols, w_dr = gridDim.x - w_dq * (unsigned)P.ncols;
+    auto advance = [&](unsigned& stream_, unsigned& col_) {
+        stream_ += w_dq;
+        col_ += w_dr;
+        if (col_ >= (unsigned)P.ncols) {
+            col_ -= (unsigned)P.ncols;
+            ++stream_;
+        }
+    };
+    auto frame_of = [&](unsigned col_, long long& j_, long long& st_, bool& staged_) {
+        j_ = P.first_col + col_;
         st_ = frame_start(P, j_);
         staged_ = LD == PK3_STAGED || (P.aligned4 && st_ >= 0 && st_ + N <= P.nsamples);
     };
-    auto stage = [&](unsigned gg) { // after a __syncthreads(): the frame's 64 KB -> buf (thread 0; nothing for a boundary frame)
-        int stream_;
+    auto stage = [&](unsigned stream_, unsigned col_) { // after a __syncthreads(): the frame's 64 KB -> buf (thread 0; nothing for a boundary frame)
         long long j_, st_;
         bool staged_;
-        frame_of(gg, stream_, j_, st_, staged_);
-        const float* src = P.samples + stream_ * P.stream_stride + ch0 * P.channel_stride + st_;
+        frame_of(col_, j_, st_, staged_);
+        const float* src = P.samples + (long long)stream_ * P.stream_stride + ch0 * P.channel_stride + st_;
         if (t == 0 && staged_) {
             mbar_expect_tx(bar, M * 8);
 #pragma unroll
@@ -204,16 +212,19 @@ JADE_KERNEL(Pk3Cfg::THREADS, 2) stft_pk3_kernel(const KParams P)
 #endif
     };
     unsigned copies = 0;
-    if (blockIdx.x < total) stage(blockIdx.x);
+    unsigned w_stream = blockIdx.x / (unsigned)P.ncols, w_col = blockIdx.x - w_stream * (unsigned)P.ncols;
+    unsigned n_stream = w_stream, n_col = w_col; // the CTA's next frame
+    if (blockIdx.x < total) stage(w_stream, w_col);
 
     // exchange-2 addresses (f2 words inside a row): element (k2, c) of a row lives at 16 k2 + 2 ((c/2 + row) & 7) + (c & 1)
     const int rotA = L3.rowA & 7, rotB = L3.rowB & 7;
 
-    for (unsigned g = blockIdx.x; g < total; g += gridDim.x) {
-        int stream;
+    for (unsigned g = blockIdx.x; g < total; g += gridDim.x, w_stream = n_stream, w_col = n_col) {
+        const int stream = (int)w_stream;
         long long j, st;
         bool staged;
-        frame_of(g, stream, j, st, staged);
+        frame_of(w_col, j, st, staged);
+        advance(n_stream, n_col);
         f2 v[32];
         // ---- pass 1: samples x window, 32-point DFT over n1, row k1 <- Y[t][k1]
         {
@@ -293,7 +304,7 @@ JADE_KERNEL(Pk3Cfg::THREADS, 2) stft_pk3_kernel(const KParams P)
             tm_wait_ld<16>(tw[0]);
             tm_tie<16>(tw[1]);
             __syncthreads(); // the matrix is free: stage the frame this CTA transforms next (covered by the rest of this one)
-            if (g + gridDim.x < total) stage(g + gridDim.x);
+            if (g + gridDim.x < total) stage(n_stream, n_col);
 #pragma unroll
             for (int d = 0; d < 2; ++d) {
                 f2 w[8];
