@@ -59,7 +59,12 @@ void run_pk_one(const KParams& P, int npal, int grid)
         if (pair_ok && !pair2) {
             const int zs = jade::PkzCfg::smem_bytes(npal), zb = jade::PkzCfg::WARPS * 32;
             if (GUARD || !P.aligned4) jade_emu::launch(jade::stft_pkz2048_kernel<true, jade::PKZ_GUARD>, grid, zb, zs, P);
-            else if (getenv("JADE_EMU_RING")) jade_emu::launch(jade::stft_pkz2048_kernel<WDB, jade::PKZ_RING>, grid, zb, zs, P); // launch_one: long evenly spaced runs
+            // (launch_one: pixel-only launches with a u8 palette take the instantiations without a clamp instruction)
+            else if (getenv("JADE_EMU_RING")) { // launch_one: long evenly spaced runs
+                if (!WDB && P.pal_u8) jade_emu::launch(jade::stft_pkz2048_kernel<false, jade::PKZ_RING, true>, grid, zb, zs, P);
+                else jade_emu::launch(jade::stft_pkz2048_kernel<WDB, jade::PKZ_RING>, grid, zb, zs, P);
+            }
+            else if (!WDB && P.pal_u8) jade_emu::launch(jade::stft_pkz2048_kernel<false, jade::PKZ_ASYNC, true>, grid, zb, zs, P);
             else jade_emu::launch(jade::stft_pkz2048_kernel<WDB, jade::PKZ_ASYNC>, grid, zb, zs, P);
         }
         else if (GUARD) jade_emu::launch(jade::stft_pk2048_kernel<MIXK, WDB, jade::PK_LD_GUARD>, grid, block, jade::PkCfgFor<MIXK>::smem_bytes(npal), P);
@@ -162,6 +167,7 @@ extern "C" int emu_render(const jade_config* cin, const int32_t* palette, int np
     P.palette = baked.data(); P.npal = npal;
     P.pmin = range.mn; P.pmax = range.mx; P.pmaxc = range.maxclamp(); P.pmult = range.mult;
     jade::colour_fold(P);
+    P.pal_u8 = (npal == 256 && baked[P.ci_hi] == baked[255] && !getenv("JADE_EMU_NO_U8")) ? 1 : 0; // as fill_params in jade_gpu.cu
     P.db_precise = c.db_precise;
     P.pooled = pooled; P.R = R; P.k_lo = k_lo; P.k_hi = k_hi; P.flip = c.flip_y;
     P.row_bins = rb.data();
@@ -270,6 +276,7 @@ extern "C" int emu_render(const jade_config* cin, const int32_t* palette, int np
                 if (Q.db) Q.db += (a - j0) * B;
                 if (part != 0) jade_emu::launch(jade::stft_pk3_kernel<true, jade::PK3_GUARD>, grid, 256, smem, Q);
                 else if (db) jade_emu::launch(jade::stft_pk3_kernel<true, jade::PK3_STAGED>, grid, 256, smem, Q);
+                else if (Q.pal_u8) jade_emu::launch(jade::stft_pk3_kernel<false, jade::PK3_STAGED, true>, grid, 256, smem, Q);
                 else jade_emu::launch(jade::stft_pk3_kernel<false, jade::PK3_STAGED>, grid, 256, smem, Q);
             }
         } else if (!general && multi != jade::MIX_SEL) {
