@@ -18,6 +18,7 @@
 // Reference lines replaced: Spectrogram.cpp:50-56,137-145 (framing, window, spectrum::power), :64-107 (mix, dB),
 // :634-647 + CColorpalette.h:32-47 (pixel loops).
 #pragma once
+#include <type_traits>
 #include "jade_pk.cuh"
 
 namespace jade {
@@ -34,7 +35,7 @@ struct PkCtaCfg {
     static constexpr int off_row = 0;
     static constexpr int off_twI = off_row + R1 * RS * 8;
     static constexpr int off_pal = off_twI + 32 * TROW * 8;
-    static JADE_HD int off_spec(int npal) { return off_pal + (npal * 4 + 15) / 16 * 16; }
+    static JADE_HD int off_spec(int npal) { return off_pal + ((npal + 1) * 4 + 15) / 16 * 16; } // palette + its `>= m_Max` entry (colour_of_lg1)
     // stft_pkcta_kernel (general == false): one mbarrier (frame staging) where the general kernels keep their spectrum
     static JADE_HD int off_bar(int npal) { return off_spec(npal); }
     static JADE_HD int smem_bytes(int npal, bool general) { return off_spec(npal) + (general ? ((B + 3) / 4) * 16 : 16); }
@@ -134,7 +135,7 @@ JADE_KERNEL(32 * R1, PkCtaCfg<R1>::MINB) stft_pkcta_kernel(const KParams P)
 
     const int t = threadIdx.x;
     stage_row_twiddles<R1>(s_twI, P.twI);
-    for (int i = t; i < P.npal; i += THREADS) s_pal[i] = P.palette[i];
+    for (int i = t; i <= P.npal; i += THREADS) s_pal[i] = P.palette[i < P.npal ? i : P.ci_hi];
     if (t == 0) mbar_init(bar, 1);
     __syncthreads();
     grid_dep_wait();
@@ -253,21 +254,27 @@ JADE_KERNEL(32 * R1, PkCtaCfg<R1>::MINB) stft_pkcta_kernel(const KParams P)
         uint32_t* p_hi = o.pix ? o.pix + t : nullptr;       // bin M - k -> row k
         float* d_lo = (WANT_DB && o.db) ? o.db + t : nullptr;
         float* d_hi = (WANT_DB && o.db) ? o.db + (M - t) : nullptr;
+        // (two copies behind a launch-uniform branch: with the u8 palette the float -> integer conversion is the clamp, colour_of_lg1)
+        auto finish = [&](auto u8) {
+            constexpr bool U8 = decltype(u8)::value;
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-            // (kept as two guarded blocks per q: the straight-line emit_bin form schedules 7 % slower here, variants run)
-            const float ll = JADE_LOG2F(MIXK == MIX_SUM ? fm(alo[q], scale, 1e-11f) : JADE_FADD(alo[q], 1e-11f));
-            const float lh = JADE_LOG2F(MIXK == MIX_SUM ? fm(ahi[q], scale, 1e-11f) : JADE_FADD(ahi[q], 1e-11f));
-            if (WANT_DB && d_lo) {
-                d_lo[THREADS * q] = JADE_FMUL(3.01029995663981195f, ll);
-                d_hi[-THREADS * q] = JADE_FMUL(3.01029995663981195f, lh);
+            for (int q = 0; q < 16; ++q) {
+                // (kept as two guarded blocks per q: the straight-line emit_bin form schedules 7 % slower here, variants run)
+                const float ll = JADE_LOG2F(MIXK == MIX_SUM ? fm(alo[q], scale, 1e-11f) : JADE_FADD(alo[q], 1e-11f));
+                const float lh = JADE_LOG2F(MIXK == MIX_SUM ? fm(ahi[q], scale, 1e-11f) : JADE_FADD(ahi[q], 1e-11f));
+                if (WANT_DB && d_lo) {
+                    d_lo[THREADS * q] = JADE_FMUL(3.01029995663981195f, ll);
+                    d_hi[-THREADS * q] = JADE_FMUL(3.01029995663981195f, lh);
+                }
+                if (p_lo) {
+                    p_lo[-THREADS * q] = colour_of_lg1<U8>(ll, P, s_pal);
+                    p_hi[THREADS * q] = colour_of_lg1<U8>(lh, P, s_pal);
+                }
             }
-            if (p_lo) {
-                p_lo[-THREADS * q] = colour_of_lg(ll, P, s_pal);
-                p_hi[THREADS * q] = colour_of_lg(lh, P, s_pal);
-            }
-        }
-        if (t == 0) emit_bin<MIXK, WANT_DB>(amid, scale, (!WANT_DB || o.pix) ? o.pix + M / 2 : nullptr, (WANT_DB && o.db) ? o.db + M / 2 : nullptr, P, s_pal);
+            if (t == 0) emit_bin1<MIXK, WANT_DB, U8, false>(amid, scale, (!WANT_DB || o.pix) ? o.pix + M / 2 : nullptr, (WANT_DB && o.db) ? o.db + M / 2 : nullptr, P, s_pal);
+        };
+        if (P.pal_u8) finish(std::true_type{});
+        else finish(std::false_type{});
     }
 }
 
