@@ -255,8 +255,12 @@ JADE_KERNEL(PkzCfg::WARPS * 32, 1) stft_pkz2048_kernel(const KParams P)
     const f2x2* trowa = reinterpret_cast<const f2x2*>(s_twa + s * Cfg::TROW);
     const f2x2* trowb = reinterpret_cast<const f2x2*>(s_twb + s * Cfg::TROW);
     const int kb = pkz_row_b(s);
-    const f2x2* rd_a = reinterpret_cast<const f2x2*>(xw + s * Cfg::XROW);
-    const f2x2* rd_b = reinterpret_cast<const f2x2*>(xw + kb * Cfg::XROW);
+    // Transpose through the warp buffer in 16-byte units {Y[s', k1], Y[s', k1']} of the two rows (k1, k1' = 64 - k1; 0 and 32) ONE
+    // lane transforms in pass 2: unit (pair u, lane s') at f2x2 index 33 u + s' (32 pairs of 32 units + 16 B pad = 16 896 B).  Lane s'
+    // writes its 64 values as 32 STS.128 (consecutive lanes, consecutive units), lane u reads its two rows as 32 LDS.128 (a quarter-
+    // warp's units 528 B apart: all 32 banks) -- 32 store instructions per frame fewer than row-wise 8-byte stores.
+    f2x2* const tr_wr = reinterpret_cast<f2x2*>(xw) + s;
+    const f2x2* const tr_rd = reinterpret_cast<const f2x2*>(xw) + 33 * s;
 
     const unsigned total = (unsigned)P.ncols * (unsigned)P.nstreams;
     const unsigned gstep = gridDim.x * WARPS;
@@ -405,16 +409,19 @@ JADE_KERNEL(PkzCfg::WARPS * 32, 1) stft_pkz2048_kernel(const KParams P)
         if (STAGED) __syncwarp(); // every lane has read its samples before the transpose overwrites them
         fft64_pk_after_stage1(v); // v[k1] = Y[s, k1]
 #pragma unroll
-        for (int k1 = 0; k1 < 64; ++k1) xw[k1 * Cfg::XROW + s] = v[k1];
+        for (int u = 0; u < 32; ++u) {
+            f2x2 t;
+            t.a = v[u];
+            t.b = v[pkz_row_b(u)];
+            tr_wr[33 * u] = t;
+        }
         __syncwarp();
         f2 ua[32], ub[32];
 #pragma unroll
-        for (int jx = 0; jx < 32; jx += 2) {
-            const f2x2 ta = rd_a[jx / 2], tb = rd_b[jx / 2];
-            ua[brev(jx, 5)] = ta.a;
-            ua[brev(jx + 1, 5)] = ta.b;
-            ub[brev(jx, 5)] = tb.a;
-            ub[brev(jx + 1, 5)] = tb.b;
+        for (int jx = 0; jx < 32; ++jx) {
+            const f2x2 t = tr_rd[jx];
+            ua[brev(jx, 5)] = t.a;
+            ub[brev(jx, 5)] = t.b;
         }
         __syncwarp(); // the buffer is free again
         const bool more = it + 1 < my_iters;
